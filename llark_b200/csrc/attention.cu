@@ -1,0 +1,529 @@
+// Causal self-attention with key-padding mask for the Llama decoder (head_dim 128), forward and backward.
+// Replaces the eager/SDPA attention inside transformers' LlamaAttention reached at m2t/models/llamav2.py:224
+// and the (declared, never wired) flash-attn-1 path m2t/llava/train/llama_flash_attn_monkey_patch.py:12-94.
+//
+// Layout: packed projections qkv [B*S, 3*NH*128] bf16 (q heads | k heads | v heads per token row, RoPE already
+// applied in place), output O [B*S, NH*128] bf16, LSE [B, NH, S] fp32 (natural log; +inf marks a fully masked row).
+// Round-1 implementation: FA2-style tiling on mma.sync m16n8k16 bf16 (fp32 accumulate, online softmax in fp32,
+// exp2 with pre-scaled log2e). Attention is 1 % of step FLOPs at S = 512; the tcgen05/TMEM
+// version is a later-round upgrade and DESIGN.md says so.
+#include "common.cuh"
+#include "../../include/llark_b200.h"
+
+namespace llark {
+
+extern thread_local int g_last_cuda_error;
+
+constexpr int HD = 128;        // head dim
+constexpr int LDS = HD + 8;    // padded smem row (272 B): conflict-free ldmatrix
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ROWS x 128 bf16 tile, global row stride gstride (elements) -> smem stride LDS; rows >= valid zero-filled.
+template <int ROWS>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long gstride, int valid) {
+    for (int i = threadIdx.x; i < ROWS * 16; i += blockDim.x) {
+        const int r = i >> 4, c = (i & 15) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < valid) v = *reinterpret_cast<const uint4*>(g + (long long)r * gstride + c);
+        *reinterpret_cast<uint4*>(s + r * LDS + c) = v;
+    }
+}
+
+// A-operand fragment address (16 rows x 16 k) for ldmatrix.x4: matrices (r0-7,k0-7) (r8-15,k0-7) (r0-7,k8-15) (r8-15,k8-15)
+__device__ __forceinline__ const __nv_bfloat16* a_addr(const __nv_bfloat16* s, int row0, int k0, int lane) {
+    return s + (row0 + (lane & 15)) * LDS + k0 + (lane >> 4) * 8;
+}
+// B operand from a [n][k]-stored tile (k contiguous), two n-blocks of 8: (n0-7,k0-7) (n0-7,k8-15) (n8-15,k0-7) (n8-15,k8-15)
+__device__ __forceinline__ const __nv_bfloat16* b_addr(const __nv_bfloat16* s, int n0, int k0, int lane) {
+    return s + (n0 + (lane & 7) + (lane >> 4) * 8) * LDS + k0 + ((lane >> 3) & 1) * 8;
+}
+// B operand from a [k][n]-stored tile (n contiguous) via .trans: (k0-7,n0-7) (k8-15,n0-7) (k0-7,n8-15) (k8-15,n8-15)
+__device__ __forceinline__ const __nv_bfloat16* bt_addr(const __nv_bfloat16* s, int k0, int n0, int lane) {
+    return s + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + n0 + (lane >> 4) * 8;
+}
+
+// =============================================================================================== forward
+// grid (ceil(S/64), NH, B), 128 threads: each warp owns 16 query rows; key tiles of 64.
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __restrict__ mask,
+                __nv_bfloat16* __restrict__ O, float* __restrict__ lse_out, int S, int NH, float scale_log2) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+    __nv_bfloat16* sK = sQ + 64 * LDS;
+    __nv_bfloat16* sV = sK + 64 * LDS;
+    float* sMask = reinterpret_cast<float*>(sV + 64 * LDS);
+
+    const int qt = gridDim.x - 1 - blockIdx.x;  // longest rows first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = qt * 64;
+    const long long rs = 3LL * NH * HD;
+    const __nv_bfloat16* qptr = qkv + ((long long)b * S + q0) * rs + (long long)h * HD;
+    const __nv_bfloat16* kbase = qkv + ((long long)b * S) * rs + (long long)NH * HD + (long long)h * HD;
+    const __nv_bfloat16* vbase = kbase + (long long)NH * HD;
+
+    load_tile<64>(sQ, qptr, rs, min(64, S - q0));
+    __syncthreads();
+    uint32_t qf[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) ldsm_x4(qf[ks], a_addr(sQ, warp * 16, ks * 16, lane));
+
+    float o[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    for (int kt = 0; kt <= qt; ++kt) {
+        const int k0 = kt * 64;
+        __syncthreads();
+        load_tile<64>(sK, kbase + (long long)k0 * rs, rs, min(64, S - k0));
+        load_tile<64>(sV, vbase + (long long)k0 * rs, rs, min(64, S - k0));
+        if (threadIdx.x < 64) {
+            const int kk = k0 + threadIdx.x;
+            const bool ok = kk < S && (!mask || mask[(long long)b * S + kk] != 0);
+            sMask[threadIdx.x] = ok ? 0.f : -INFINITY;
+        }
+        __syncthreads();
+
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[i][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t kb[4];
+                ldsm_x4(kb, b_addr(sK, j * 16, ks * 16, lane));
+                mma16816(s[2 * j], qf[ks], kb[0], kb[1]);
+                mma16816(s[2 * j + 1], qf[ks], kb[2], kb[3]);
+            }
+        }
+        float rmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = nb * 8 + (lane & 3) * 2 + (e & 1);
+                const int row = warp * 16 + (lane >> 2) + (e >> 1) * 8;
+                float v = s[nb][e] * scale_log2 + sMask[col];
+                if (kt == qt && col > row) v = -INFINITY;
+                s[nb][e] = v;
+                rmax[e >> 1] = fmaxf(rmax[e >> 1], v);
+            }
+        }
+        float alpha[2], m_use[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+            const float m_new = fmaxf(m_run[r], rmax[r]);
+            m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+            alpha[r] = exp2f(m_run[r] - m_use[r]);
+            m_run[r] = m_new;
+            l_run[r] *= alpha[r];
+        }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = exp2f(s[nb][e] - m_use[e >> 1]);
+                s[nb][e] = p;
+                l_run[e >> 1] += p;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+            o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+        }
+#pragma unroll
+        for (int ks2 = 0; ks2 < 4; ++ks2) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * ks2][0], s[2 * ks2][1]);
+            pa[1] = pack_bf16x2(s[2 * ks2][2], s[2 * ks2][3]);
+            pa[2] = pack_bf16x2(s[2 * ks2 + 1][0], s[2 * ks2 + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * ks2 + 1][2], s[2 * ks2 + 1][3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t vb[4];
+                ldsm_x4_t(vb, bt_addr(sV, ks2 * 16, j * 16, lane));
+                mma16816(o[2 * j], pa, vb[0], vb[1]);
+                mma16816(o[2 * j + 1], pa, vb[2], vb[3]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+        if (row >= S) continue;
+        const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+        __nv_bfloat16* optr = O + ((long long)b * S + row) * ((long long)NH * HD) + (long long)h * HD;
+#pragma unroll
+        for (int nb = 0; nb < 16; ++nb) {
+            const int col = nb * 8 + (lane & 3) * 2;
+            *reinterpret_cast<uint32_t*>(optr + col) = pack_bf16x2(o[nb][2 * r] * inv, o[nb][2 * r + 1] * inv);
+        }
+        if ((lane & 3) == 0)
+            lse_out[((long long)b * NH + h) * S + row] =
+                l_run[r] > 0.f ? m_run[r] * LN2 + logf(l_run[r]) : INFINITY;
+    }
+}
+
+// =============================================================================================== backward
+// Dsum[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (b,s,h).
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                                     float* __restrict__ Dsum, long long B, int S, int NH) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = B * S * NH;
+    if (w >= total) return;
+    const int h = (int)(w % NH);
+    const long long bs = w / NH;
+    const long long off = bs * ((long long)NH * HD) + (long long)h * HD + lane * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(O + off);
+    const uint2 d = *reinterpret_cast<const uint2*>(dO + off);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
+    float s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y;
+    s = warp_sum(s);
+    if (lane == 0) {
+        const long long b = bs / S;
+        const int sidx = (int)(bs % S);
+        Dsum[(b * NH + h) * S + sidx] = s;
+    }
+}
+
+// dK, dV: grid (ceil(S/64) key tiles, NH, B), 128 threads; each warp owns 16 keys; query blocks of 32.
+__global__ void __launch_bounds__(128)
+attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __restrict__ mask,
+                     const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
+                     const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH,
+                     float scale, float scale_log2) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+    __nv_bfloat16* sV = sK + 64 * LDS;
+    __nv_bfloat16* sQ = sV + 64 * LDS;
+    __nv_bfloat16* sdO = sQ + 32 * LDS;
+    float* sLse = reinterpret_cast<float*>(sdO + 32 * LDS);  // 32, log2 domain
+    float* sD = sLse + 32;
+
+    const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = kt * 64;
+    const long long rs = 3LL * NH * HD;
+    const long long os = (long long)NH * HD;
+    const __nv_bfloat16* qbase = qkv + ((long long)b * S) * rs + (long long)h * HD;
+    const __nv_bfloat16* kptr = qbase + (long long)NH * HD + (long long)k0 * rs;
+    const __nv_bfloat16* vptr = kptr + (long long)NH * HD;
+    const __nv_bfloat16* dobase = dO + ((long long)b * S) * os + (long long)h * HD;
+
+    load_tile<64>(sK, kptr, rs, min(64, S - k0));
+    load_tile<64>(sV, vptr, rs, min(64, S - k0));
+
+    // key validity for this thread's two key rows (g, g+8)
+    bool kvalid[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int kk = k0 + warp * 16 + (lane >> 2) + r * 8;
+        kvalid[r] = kk < S && (!mask || mask[(long long)b * S + kk] != 0);
+    }
+
+    float dk[16][4], dv[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
+
+    for (int q0 = k0; q0 < S; q0 += 32) {
+        __syncthreads();
+        load_tile<32>(sQ, qbase + (long long)q0 * rs, rs, min(32, S - q0));
+        load_tile<32>(sdO, dobase + (long long)q0 * os, os, min(32, S - q0));
+        if (threadIdx.x < 32) {
+            const int qq = q0 + threadIdx.x;
+            const bool ok = qq < S;
+            sLse[threadIdx.x] = ok ? lse[((long long)b * NH + h) * S + qq] * LOG2E : INFINITY;
+            sD[threadIdx.x] = ok ? Dsum[((long long)b * NH + h) * S + qq] : 0.f;
+        }
+        __syncthreads();
+
+        // S^T = K Q^T  (16 keys x 32 queries), dP^T = V dO^T
+        float st[4][4], dpt[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) st[i][e] = dpt[i][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t ka[4], va[4];
+            ldsm_x4(ka, a_addr(sK, warp * 16, ks * 16, lane));
+            ldsm_x4(va, a_addr(sV, warp * 16, ks * 16, lane));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t qb[4], db[4];
+                ldsm_x4(qb, b_addr(sQ, j * 16, ks * 16, lane));
+                ldsm_x4(db, b_addr(sdO, j * 16, ks * 16, lane));
+                mma16816(st[2 * j], ka, qb[0], qb[1]);
+                mma16816(st[2 * j + 1], ka, qb[2], qb[3]);
+                mma16816(dpt[2 * j], va, db[0], db[1]);
+                mma16816(dpt[2 * j + 1], va, db[2], db[3]);
+            }
+        }
+        // P^T and dS^T
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int qc = nb * 8 + (lane & 3) * 2 + (e & 1);  // query within block
+                const int kr = warp * 16 + (lane >> 2) + (e >> 1) * 8;  // key within tile
+                const bool allowed = kvalid[e >> 1] && (q0 + qc >= k0 + kr);
+                const float p = allowed ? exp2f(st[nb][e] * scale_log2 - sLse[qc]) : 0.f;
+                st[nb][e] = p;
+                dpt[nb][e] = p * (dpt[nb][e] - sD[qc]);
+            }
+        }
+        // dV += P^T dO ; dK += dS^T Q    (k = 32 queries -> 2 k-steps)
+#pragma unroll
+        for (int ks2 = 0; ks2 < 2; ++ks2) {
+            uint32_t pa[4], sa[4];
+            pa[0] = pack_bf16x2(st[2 * ks2][0], st[2 * ks2][1]);
+            pa[1] = pack_bf16x2(st[2 * ks2][2], st[2 * ks2][3]);
+            pa[2] = pack_bf16x2(st[2 * ks2 + 1][0], st[2 * ks2 + 1][1]);
+            pa[3] = pack_bf16x2(st[2 * ks2 + 1][2], st[2 * ks2 + 1][3]);
+            sa[0] = pack_bf16x2(dpt[2 * ks2][0], dpt[2 * ks2][1]);
+            sa[1] = pack_bf16x2(dpt[2 * ks2][2], dpt[2 * ks2][3]);
+            sa[2] = pack_bf16x2(dpt[2 * ks2 + 1][0], dpt[2 * ks2 + 1][1]);
+            sa[3] = pack_bf16x2(dpt[2 * ks2 + 1][2], dpt[2 * ks2 + 1][3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t ob[4], qb[4];
+                ldsm_x4_t(ob, bt_addr(sdO, ks2 * 16, j * 16, lane));
+                ldsm_x4_t(qb, bt_addr(sQ, ks2 * 16, j * 16, lane));
+                mma16816(dv[2 * j], pa, ob[0], ob[1]);
+                mma16816(dv[2 * j + 1], pa, ob[2], ob[3]);
+                mma16816(dk[2 * j], sa, qb[0], qb[1]);
+                mma16816(dk[2 * j + 1], sa, qb[2], qb[3]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int kk = k0 + warp * 16 + (lane >> 2) + r * 8;
+        if (kk >= S) continue;
+        __nv_bfloat16* dkp = dqkv + ((long long)b * S + kk) * rs + (long long)NH * HD + (long long)h * HD;
+        __nv_bfloat16* dvp = dkp + (long long)NH * HD;
+#pragma unroll
+        for (int nb = 0; nb < 16; ++nb) {
+            const int col = nb * 8 + (lane & 3) * 2;
+            *reinterpret_cast<uint32_t*>(dkp + col) = pack_bf16x2(dk[nb][2 * r] * scale, dk[nb][2 * r + 1] * scale);
+            *reinterpret_cast<uint32_t*>(dvp + col) = pack_bf16x2(dv[nb][2 * r], dv[nb][2 * r + 1]);
+        }
+    }
+}
+
+// dQ: grid (ceil(S/64) query tiles, NH, B), 128 threads; each warp owns 16 queries; key tiles of 64.
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __restrict__ mask,
+                   const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
+                   const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
+                   float scale_log2) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+    __nv_bfloat16* sdO = sQ + 64 * LDS;
+    __nv_bfloat16* sK = sdO + 64 * LDS;
+    __nv_bfloat16* sV = sK + 64 * LDS;
+    float* sMask = reinterpret_cast<float*>(sV + 64 * LDS);  // 64: 1 = key allowed
+
+    const int qt = gridDim.x - 1 - blockIdx.x;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = qt * 64;
+    const long long rs = 3LL * NH * HD;
+    const long long os = (long long)NH * HD;
+    const __nv_bfloat16* qptr = qkv + ((long long)b * S + q0) * rs + (long long)h * HD;
+    const __nv_bfloat16* kbase = qkv + ((long long)b * S) * rs + (long long)NH * HD + (long long)h * HD;
+    const __nv_bfloat16* vbase = kbase + (long long)NH * HD;
+    const __nv_bfloat16* doptr = dO + ((long long)b * S + q0) * os + (long long)h * HD;
+
+    load_tile<64>(sQ, qptr, rs, min(64, S - q0));
+    load_tile<64>(sdO, doptr, os, min(64, S - q0));
+
+    float lse2[2], dsum[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+        const bool ok = row < S;
+        lse2[r] = ok ? lse[((long long)b * NH + h) * S + row] * LOG2E : INFINITY;
+        dsum[r] = ok ? Dsum[((long long)b * NH + h) * S + row] : 0.f;
+    }
+
+    float dq[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dq[i][e] = 0.f;
+
+    for (int kt = 0; kt <= qt; ++kt) {
+        const int k0 = kt * 64;
+        __syncthreads();
+        load_tile<64>(sK, kbase + (long long)k0 * rs, rs, min(64, S - k0));
+        load_tile<64>(sV, vbase + (long long)k0 * rs, rs, min(64, S - k0));
+        if (threadIdx.x < 64) {
+            const int kk = k0 + threadIdx.x;
+            sMask[threadIdx.x] = (kk < S && (!mask || mask[(long long)b * S + kk] != 0)) ? 1.f : 0.f;
+        }
+        __syncthreads();
+
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[i][e] = dp[i][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t qa[4], da[4];
+            ldsm_x4(qa, a_addr(sQ, warp * 16, ks * 16, lane));
+            ldsm_x4(da, a_addr(sdO, warp * 16, ks * 16, lane));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t kb[4], vb[4];
+                ldsm_x4(kb, b_addr(sK, j * 16, ks * 16, lane));
+                ldsm_x4(vb, b_addr(sV, j * 16, ks * 16, lane));
+                mma16816(s[2 * j], qa, kb[0], kb[1]);
+                mma16816(s[2 * j + 1], qa, kb[2], kb[3]);
+                mma16816(dp[2 * j], da, vb[0], vb[1]);
+                mma16816(dp[2 * j + 1], da, vb[2], vb[3]);
+            }
+        }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = nb * 8 + (lane & 3) * 2 + (e & 1);
+                const int row = warp * 16 + (lane >> 2) + (e >> 1) * 8;
+                const bool allowed = sMask[col] != 0.f && !(kt == qt && col > row);
+                const float p = allowed ? exp2f(s[nb][e] * scale_log2 - lse2[e >> 1]) : 0.f;
+                s[nb][e] = p * (dp[nb][e] - dsum[e >> 1]);  // dS
+            }
+        }
+#pragma unroll
+        for (int ks2 = 0; ks2 < 4; ++ks2) {
+            uint32_t sa[4];
+            sa[0] = pack_bf16x2(s[2 * ks2][0], s[2 * ks2][1]);
+            sa[1] = pack_bf16x2(s[2 * ks2][2], s[2 * ks2][3]);
+            sa[2] = pack_bf16x2(s[2 * ks2 + 1][0], s[2 * ks2 + 1][1]);
+            sa[3] = pack_bf16x2(s[2 * ks2 + 1][2], s[2 * ks2 + 1][3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t kb[4];
+                ldsm_x4_t(kb, bt_addr(sK, ks2 * 16, j * 16, lane));
+                mma16816(dq[2 * j], sa, kb[0], kb[1]);
+                mma16816(dq[2 * j + 1], sa, kb[2], kb[3]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+        if (row >= S) continue;
+        __nv_bfloat16* dqp = dqkv + ((long long)b * S + row) * rs + (long long)h * HD;
+#pragma unroll
+        for (int nb = 0; nb < 16; ++nb) {
+            const int col = nb * 8 + (lane & 3) * 2;
+            *reinterpret_cast<uint32_t*>(dqp + col) = pack_bf16x2(dq[nb][2 * r] * scale, dq[nb][2 * r + 1] * scale);
+        }
+    }
+}
+
+constexpr int FWD_SMEM = 3 * 64 * LDS * 2 + 64 * 4;
+constexpr int DKDV_SMEM = (2 * 64 + 2 * 32) * LDS * 2 + 64 * 4;
+constexpr int DQ_SMEM = 4 * 64 * LDS * 2 + 64 * 4;
+
+static int set_smem(const void* fn, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_ECUDA;
+    }
+    return LLARK_OK;
+}
+static inline int check_launch2() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_ECUDA;
+    }
+    return LLARK_OK;
+}
+
+}  // namespace llark
+
+using namespace llark;
+
+extern "C" int llark_attn_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S,
+                              int n_heads, int head_dim, float scale, cudaStream_t st) {
+    if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0) return LLARK_EINVAL;
+    int rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM);
+    if (rc) return rc;
+    dim3 grid((S + 63) / 64, n_heads, B);
+    attn_fwd_kernel<<<grid, 128, FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, key_mask, (__nv_bfloat16*)out, lse, S,
+                                                  n_heads, scale * LOG2E);
+    return check_launch2();
+}
+
+extern "C" long long llark_attn_bwd_workspace(int B, int S, int n_heads) {
+    return (long long)B * S * n_heads * (long long)sizeof(float);
+}
+
+extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                              const float* lse, void* dqkv, int B, int S, int n_heads, int head_dim, float scale,
+                              void* workspace, cudaStream_t st) {
+    if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0 || !workspace) return LLARK_EINVAL;
+    float* Dsum = (float*)workspace;
+    const long long warps = (long long)B * S * n_heads;
+    attn_bwd_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out,
+                                                                                (const __nv_bfloat16*)dout, Dsum, B, S,
+                                                                                n_heads);
+    int rc = check_launch2();
+    if (rc) return rc;
+    rc = set_smem((const void*)attn_bwd_dkdv_kernel, DKDV_SMEM);
+    if (rc) return rc;
+    rc = set_smem((const void*)attn_bwd_dq_kernel, DQ_SMEM);
+    if (rc) return rc;
+    dim3 grid((S + 63) / 64, n_heads, B);
+    attn_bwd_dkdv_kernel<<<grid, 128, DKDV_SMEM, st>>>((const __nv_bfloat16*)qkv, key_mask, (const __nv_bfloat16*)dout,
+                                                       lse, Dsum, (__nv_bfloat16*)dqkv, S, n_heads, scale, scale * LOG2E);
+    rc = check_launch2();
+    if (rc) return rc;
+    attn_bwd_dq_kernel<<<grid, 128, DQ_SMEM, st>>>((const __nv_bfloat16*)qkv, key_mask, (const __nv_bfloat16*)dout, lse,
+                                                   Dsum, (__nv_bfloat16*)dqkv, S, n_heads, scale, scale * LOG2E);
+    return check_launch2();
+}

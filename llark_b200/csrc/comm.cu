@@ -1,0 +1,60 @@
+// Data-parallel exchange step of the LLark training path: ONE ncclAllReduce(sum, bf16) over the flat gradient
+// bucket per optimizer step (reference: HF Trainer + DDP under torch.distributed.launch,
+// scripts/training/train_llark.sh:20-22,44). The 1/(world*accum) scale and the
+// global-norm clip are fused into the AdamW kernel that consumes the reduced bucket (llama_ops.cu).
+// Large buckets are split into chunks so the caller can enqueue them on a comm stream while wgrad kernels of
+// earlier layers are still running.
+#include "common.cuh"
+#include <nccl.h>
+#include <string.h>
+
+namespace llark {
+extern thread_local int g_last_cuda_error;
+}
+using namespace llark;
+
+extern "C" int llark_comm_unique_id(void* id128_host) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) {
+        g_last_cuda_error = (int)r;
+        return LLARK_ENCCL;
+    }
+    memcpy(id128_host, &id, sizeof(id));
+    return LLARK_OK;
+}
+
+extern "C" int llark_comm_init(void** comm_out, const void* id128_host, int world, int rank) {
+    if (!comm_out || !id128_host || world <= 0 || rank < 0 || rank >= world) return LLARK_EINVAL;
+    ncclUniqueId id;
+    memcpy(&id, id128_host, sizeof(id));
+    ncclComm_t comm;
+    ncclResult_t r = ncclCommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) {
+        g_last_cuda_error = (int)r;
+        return LLARK_ENCCL;
+    }
+    *comm_out = (void*)comm;
+    return LLARK_OK;
+}
+
+extern "C" int llark_comm_destroy(void* comm) {
+    if (!comm) return LLARK_OK;
+    ncclResult_t r = ncclCommDestroy((ncclComm_t)comm);
+    if (r != ncclSuccess) {
+        g_last_cuda_error = (int)r;
+        return LLARK_ENCCL;
+    }
+    return LLARK_OK;
+}
+
+extern "C" int llark_grad_bucket_allreduce(void* comm, void* grads_bf16, long long n, cudaStream_t stream) {
+    if (!comm || !grads_bf16 || n <= 0) return LLARK_EINVAL;
+    ncclResult_t r = ncclAllReduce(grads_bf16, grads_bf16, (size_t)n, ncclBfloat16, ncclSum, (ncclComm_t)comm, stream);
+    if (r != ncclSuccess) {
+        g_last_cuda_error = (int)r;
+        return LLARK_ENCCL;
+    }
+    return LLARK_OK;
+}

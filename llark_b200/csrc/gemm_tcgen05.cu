@@ -1,0 +1,472 @@
+// llark_b200 GEMM core: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ R[M,N]),  fp32 accumulate in TMEM.
+//
+// Replaces every cuBLAS `addmm`/`Linear` call on the reference hot path:
+// reference call sites m2t/models/llamav2.py:133 (mm_projector), :224 (LlamaModel q/k/v/o/gate/up/down),
+// :312 (lm_head), their autograd dgrad/wgrad, and jukebox/main.py:108 (prior c_attn/c_proj/mlp).
+//
+// Design (one CTA per SM, 256 threads):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1   : MMA issuer    (one lane issues tcgen05.mma kind::f16 / kind::tf32, M=128, N=256, K=32 bytes)
+//   warp 2   : TMEM allocator (512 columns = two 128x256 fp32 accumulator stages)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> bias/residual -> bf16/fp32 -> 16 B global stores)
+// The smem ring has kStages stages of (A 16 KB + B 32 KB); the two TMEM accumulator stages let the MMA
+// of tile i+1 overlap the epilogue of tile i. Operands may be K-major or MN-major (dgrad/wgrad read the
+// weights / activations in place, no transposes), selected per operand through the UMMA descriptors.
+#include "common.cuh"
+#include "../../include/llark_b200.h"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+#include <stdio.h>
+
+namespace llark {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_KB = 128;  // bytes of K per smem row == swizzle width
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kThreads = 256;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_KB;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_KB;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+    int M, N, K;
+    void* C;
+    long long ldc;
+    int c_fp32;
+    const void* bias;  // bf16 [N] (or fp32 when bias_fp32)
+    int bias_fp32;
+    const void* R;  // residual, same dtype as C
+    long long ldr;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+    int elem_bytes;  // 2 (bf16) or 4 (tf32)
+};
+
+// SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TileCoord {
+    int m_blk, n_blk;
+};
+// Grouped rasterisation: 16 m-blocks share a sweep over n so that the ~148 tiles in flight reuse
+// A/B panels out of L2.
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks) {
+    constexpr int GROUP_M = 16;
+    const int tiles_per_group = GROUP_M * num_n_blocks;
+    const int group = tile / tiles_per_group;
+    const int first_m = group * GROUP_M;
+    const int group_m = min(GROUP_M, num_m_blocks - first_m);
+    const int in_group = tile - group * tiles_per_group;
+    TileCoord t;
+    t.m_blk = first_m + in_group % group_m;
+    t.n_blk = in_group / group_m;
+    return t;
+}
+
+template <int A_MN, int B_MN, int TF32>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + kAccStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int elems_per_row = BLOCK_KB / p.elem_bytes;  // K elements per 128 B smem row (64 bf16 / 32 tf32)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_base_slot, kAccStages * BLOCK_N);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                const int k0 = kb * elems_per_row;
+                if (A_MN == 0) {
+                    tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {K=128B, 128 rows}
+                } else {
+                    // A stored [K][M]: boxes of {64 M-elements (128 B), elems_per_row K rows}
+                    constexpr int MN_PER_BOX_BYTES = 128;
+                    const int mn_per_box = MN_PER_BOX_BYTES / p.elem_bytes;
+                    const int box_bytes = elems_per_row * 128;
+                    for (int j = 0; j < BLOCK_M / mn_per_box; ++j)
+                        tma_load_2d(sa + j * box_bytes, &tma_a, &full_bar[stage], m0 + j * mn_per_box, k0);
+                }
+                if (B_MN == 0) {
+                    tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);  // box {K=128B, 256 rows}
+                } else {
+                    const int mn_per_box = 128 / p.elem_bytes;
+                    const int box_bytes = elems_per_row * 128;
+                    for (int j = 0; j < BLOCK_N / mn_per_box; ++j)
+                        tma_load_2d(sb + j * box_bytes, &tma_b, &full_bar[stage], n0 + j * mn_per_box, k0);
+                }
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 @4, a/b format @7/@10
+        // (BF16 = 1, TF32 = 2), a_major @15, b_major @16, N>>3 @17, M>>4 @24.
+        const uint32_t fmt = TF32 ? 2u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+        // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+        // MN-major SW128: 128 B of MN per row, 8 K-rows per 1024 B group (SBO), next 128 B MN chunk LBO apart.
+        const uint32_t mn_box_bytes = elems_per_row * 128;
+        const uint32_t a_lbo = A_MN ? mn_box_bytes : 0, b_lbo = B_MN ? mn_box_bytes : 0;
+        // one UMMA consumes 32 bytes of K: K-major -> +32 B inside the swizzle row; MN-major -> +(32/elem) rows
+        const uint32_t k_rows_per_mma = 32 / p.elem_bytes;
+        const uint32_t a_kstep = A_MN ? (k_rows_per_mma * 128) >> 4 : (32 >> 4);
+        const uint32_t b_kstep = B_MN ? (k_rows_per_mma * 128) >> 4 : (32 >> 4);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t sb = sa + A_STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
+                const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+                for (int k = 0; k < BLOCK_KB / 32; ++k) {
+                    const uint64_t ad = adesc + (uint64_t)(k * a_kstep);
+                    const uint64_t bd = bdesc + (uint64_t)(k * b_kstep);
+                    if (TF32)
+                        umma_tf32(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                    else
+                        umma_f16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;  // TMEM lane quadrant
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)tc.m_blk * BLOCK_M + ew * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                const int col0 = tc.n_blk * BLOCK_N + c * 32;
+                if (col0 >= p.N) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * 32, v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col = col0 + j * 8;
+                    if (col >= p.N) break;
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+                    const bool full8 = (col + 8 <= p.N);
+                    if (p.bias) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (full8 || col + e < p.N)
+                                f[e] += p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[col + e]
+                                                    : __bfloat162float(
+                                                          reinterpret_cast<const __nv_bfloat16*>(p.bias)[col + e]);
+                    }
+                    if (p.c_fp32) {
+                        float* cptr = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
+                        if (p.R) {
+                            const float* rptr = reinterpret_cast<const float*>(p.R) + row * p.ldr + col;
+                            if (full8) {
+                                const float4 r0 = *reinterpret_cast<const float4*>(rptr);
+                                const float4 r1 = *reinterpret_cast<const float4*>(rptr + 4);
+                                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                            } else {
+                                for (int e = 0; e < 8; ++e)
+                                    if (col + e < p.N) f[e] += rptr[e];
+                            }
+                        }
+                        if (full8) {
+                            *reinterpret_cast<float4*>(cptr) = make_float4(f[0], f[1], f[2], f[3]);
+                            *reinterpret_cast<float4*>(cptr + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                        } else {
+                            for (int e = 0; e < 8; ++e)
+                                if (col + e < p.N) cptr[e] = f[e];
+                        }
+                    } else {
+                        __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
+                        if (p.R) {
+                            const __nv_bfloat16* rptr = reinterpret_cast<const __nv_bfloat16*>(p.R) + row * p.ldr + col;
+                            if (full8) {
+                                const uint4 r = *reinterpret_cast<const uint4*>(rptr);
+                                const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c2 = unpack_bf16x2(r.z),
+                                             d = unpack_bf16x2(r.w);
+                                f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+                                f[4] += c2.x; f[5] += c2.y; f[6] += d.x; f[7] += d.y;
+                            } else {
+                                for (int e = 0; e < 8; ++e)
+                                    if (col + e < p.N) f[e] += __bfloat162float(rptr[e]);
+                            }
+                        }
+                        if (full8) {
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]);
+                            o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]);
+                            o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(cptr) = o;
+                        } else {
+                            for (int e = 0; e < 8; ++e)
+                                if (col + e < p.N) cptr[e] = __float2bfloat16_rn(f[e]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kAccStages * BLOCK_N);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static std::mutex g_mu;
+thread_local int g_last_cuda_error = 0;
+
+static int ensure_driver() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_encode) return LLARK_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_EDRIVER;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    return LLARK_OK;
+}
+
+struct MapKey {
+    const void* ptr;
+    long long inner, outer, ld;
+    int box_inner, box_outer, elem;
+    bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+        return (size_t)h;
+    }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// 2-D tensor map over a row-major [outer][ld] array of which [outer][inner] is valid; 128 B swizzle.
+static int get_tensor_map(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld,
+                          int box_inner, int box_outer, int elem_bytes) {
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.inner = inner; key.outer = outer; key.ld = ld;
+    key.box_inner = box_inner; key.box_outer = box_outer; key.elem = elem_bytes;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto itf = g_map_cache.find(key);
+        if (itf != g_map_cache.end()) {
+            *out = itf->second;
+            return LLARK_OK;
+        }
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) return LLARK_EINVAL;
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t gstride[1] = {(cuuint64_t)(ld * elem_bytes)};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return LLARK_EDRIVER;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();
+    g_map_cache[key] = *out;
+    return LLARK_OK;
+}
+
+template <int A_MN, int B_MN, int TF32>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas, cudaStream_t stream) {
+    static bool attr_set = false;
+    auto kfn = gemm_kernel<A_MN, B_MN, TF32>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            g_last_cuda_error = (int)e;
+            return LLARK_ECUDA;
+        }
+        attr_set = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    kfn<<<grid, kThreads, SMEM_BYTES, stream>>>(ta, tb, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_ECUDA;
+    }
+    return LLARK_OK;
+}
+
+}  // namespace llark
+
+using namespace llark;
+
+extern "C" int llark_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
+                          void* C, long long ldc, int c_fp32, const void* bias, int bias_fp32, const void* R,
+                          long long ldr, int M, int N, int K, int in_fp32, int max_ctas, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return LLARK_EINVAL;
+    int rc = ensure_driver();
+    if (rc != LLARK_OK) return rc;
+    const int eb = in_fp32 ? 4 : 2;
+    const int epr = BLOCK_KB / eb;  // K elements per smem row
+    const int vec = c_fp32 ? 4 : 8;
+    if ((ldc % vec) != 0 || (reinterpret_cast<uintptr_t>(C) & 15) != 0) return LLARK_EINVAL;
+    if (R && ((ldr % vec) != 0 || (reinterpret_cast<uintptr_t>(R) & 15) != 0)) return LLARK_EINVAL;
+
+    CUtensorMap ta, tb;
+    if (!a_mn_major)
+        rc = get_tensor_map(&ta, A, K, M, lda, epr, BLOCK_M, eb);  // [M][K], box {K-row 128 B, 128 rows}
+    else
+        rc = get_tensor_map(&ta, A, M, K, lda, epr, epr, eb);  // [K][M], box {128 B of M, epr K-rows}
+    if (rc != LLARK_OK) return rc;
+    if (!b_mn_major)
+        rc = get_tensor_map(&tb, B, K, N, ldb, epr, BLOCK_N, eb);
+    else
+        rc = get_tensor_map(&tb, B, N, K, ldb, epr, epr, eb);
+    if (rc != LLARK_OK) return rc;
+
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
+    p.bias = bias; p.bias_fp32 = bias_fp32;
+    p.R = R; p.ldr = ldr;
+    p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+    p.num_k_blocks = (K + epr - 1) / epr;
+    p.elem_bytes = eb;
+
+    const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+    if (!in_fp32) {
+        switch (sel) {
+            case 0: return launch<0, 0, 0>(ta, tb, p, max_ctas, stream);
+            case 1: return launch<0, 1, 0>(ta, tb, p, max_ctas, stream);
+            case 2: return launch<1, 0, 0>(ta, tb, p, max_ctas, stream);
+            default: return launch<1, 1, 0>(ta, tb, p, max_ctas, stream);
+        }
+    } else {
+        switch (sel) {
+            case 0: return launch<0, 0, 1>(ta, tb, p, max_ctas, stream);
+            case 1: return launch<0, 1, 1>(ta, tb, p, max_ctas, stream);
+            case 2: return launch<1, 0, 1>(ta, tb, p, max_ctas, stream);
+            default: return launch<1, 1, 1>(ta, tb, p, max_ctas, stream);
+        }
+    }
+}
+
+// Tensor maps are cached by (pointer, shape): callers that free and re-allocate buffers at the same address
+// with another shape get a different key, so the cache is only ever an optimisation. Exposed for tests.
+extern "C" void llark_gemm_clear_cache(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_map_cache.clear();
+}

@@ -1,0 +1,259 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/llark_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every op below passes raw device
+pointers + the stream to libllark_b200.so. There is no eager/PyTorch fallback: on a machine without the built
+extension or without a GPU these raise.
+"""
+import ctypes
+import math
+
+import torch
+
+from ._lib import check, lib
+
+BF16 = torch.bfloat16
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError("llark_b200 ops need CUDA tensors (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_dtype=None, bias=None,
+         residual=None, lda=None, ldb=None, ldc=None, ldr=None, max_ctas=0):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (+residual).
+
+    a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True); row-major with
+    leading dimension = last-dim stride unless lda/ldb given. bf16 inputs use kind::f16, fp32 inputs kind::tf32.
+    """
+    _req(a), _req(b)
+    in_fp32 = a.dtype == torch.float32
+    if a.dtype != b.dtype or a.dtype not in (BF16, torch.float32):
+        raise TypeError("gemm inputs must both be bf16 or both fp32")
+    if M is None:
+        M = a.shape[1] if a_mn else a.shape[0]
+    if K is None:
+        K = a.shape[0] if a_mn else a.shape[1]
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+    lda = lda if lda is not None else a.stride(0)
+    ldb = ldb if ldb is not None else b.stride(0)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype or (torch.float32 if in_fp32 else BF16))
+    ldc = ldc if ldc is not None else out.stride(0)
+    c_fp32 = out.dtype == torch.float32
+    if residual is not None:
+        if residual.dtype != out.dtype:
+            raise TypeError("residual dtype must equal output dtype")
+        ldr = ldr if ldr is not None else residual.stride(0)
+    else:
+        ldr = 0
+    bias_fp32 = bias is not None and bias.dtype == torch.float32
+    rc = lib().llark_gemm(_p(a), int(a_mn), lda, _p(b), int(b_mn), ldb, _p(out), ldc, int(c_fp32), _p(bias),
+                          int(bias_fp32), _p(residual), ldr, M, N, K, int(in_fp32), max_ctas, _stream())
+    check(rc, f"llark_gemm(M={M},N={N},K={K})")
+    return out
+
+
+def cast_f32_to_bf16(x, out=None):
+    _req(x, torch.float32)
+    x = x.contiguous()
+    out = out if out is not None else torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(lib().llark_cast_f32_to_bf16(_p(x), _p(out), x.numel(), _stream()), "cast_f32_to_bf16")
+    return out
+
+
+def cast_bf16_to_f32(x, out=None):
+    _req(x, BF16)
+    x = x.contiguous()
+    out = out if out is not None else torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    check(lib().llark_cast_bf16_to_f32(_p(x), _p(out), x.numel(), _stream()), "cast_bf16_to_f32")
+    return out
+
+
+def splice_scan(ids, start_id, end_id, frames, start_pos, flags):
+    B, S = ids.shape
+    check(lib().llark_splice_scan(_p(ids), B, S, start_id, end_id, _p(frames), _p(start_pos), _p(flags), _stream()),
+          "splice_scan")
+
+
+def embed_splice_fwd(ids, table, audio, audio_off, frames, start_pos, out):
+    B, S = ids.shape
+    H = table.shape[1]
+    check(lib().llark_embed_splice_fwd(_p(ids), _p(table), _p(audio), _p(audio_off), _p(frames), _p(start_pos),
+                                       _p(out), B, S, H, table.shape[0], _stream()), "embed_splice_fwd")
+    return out
+
+
+def embed_splice_bwd(ids, dout, daudio, audio_off, frames, start_pos, dtable, vocab, detach_text):
+    B, S = ids.shape
+    H = dout.shape[-1]
+    check(lib().llark_embed_splice_bwd(_p(ids), _p(dout), _p(daudio), _p(audio_off), _p(frames), _p(start_pos),
+                                       _p(dtable), B, S, H, vocab, int(detach_text), _stream()), "embed_splice_bwd")
+
+
+def rmsnorm_fwd(x, w, eps, y=None, rstd=None):
+    rows, H = x.shape
+    y = y if y is not None else torch.empty_like(x)
+    check(lib().llark_rmsnorm_fwd(_p(x), _p(w), _p(y), _p(rstd), rows, H, eps, _stream()), "rmsnorm_fwd")
+    return y
+
+
+def rmsnorm_bwd(x, w, dy, rstd, dres, dx, dw, accumulate_dw, workspace):
+    rows, H = x.shape
+    need = lib().llark_rmsnorm_bwd_workspace(rows, H)
+    if workspace.numel() * workspace.element_size() < need:
+        raise RuntimeError("rmsnorm_bwd workspace too small")
+    check(lib().llark_rmsnorm_bwd(_p(x), _p(w), _p(dy), _p(rstd), _p(dres), _p(dx), _p(dw), int(accumulate_dw), rows,
+                                  H, _p(workspace), _stream()), "rmsnorm_bwd")
+    return dx
+
+
+def rope_(qkv, cos_t, sin_t, S, n_heads, D, inverse=False):
+    rows = qkv.shape[0]
+    check(lib().llark_rope(_p(qkv), _p(cos_t), _p(sin_t), rows, S, n_heads, D, qkv.stride(0), int(inverse), _stream()),
+          "rope")
+    return qkv
+
+
+def swiglu_fwd(gu, act=None):
+    rows, I2 = gu.shape
+    act = act if act is not None else torch.empty((rows, I2 // 2), device=gu.device, dtype=BF16)
+    check(lib().llark_swiglu_fwd(_p(gu), _p(act), rows, I2 // 2, _stream()), "swiglu_fwd")
+    return act
+
+
+def swiglu_bwd(gu, dact, dgu=None):
+    rows, I2 = gu.shape
+    dgu = dgu if dgu is not None else torch.empty_like(gu)
+    check(lib().llark_swiglu_bwd(_p(gu), _p(dact), _p(dgu), rows, I2 // 2, _stream()), "swiglu_bwd")
+    return dgu
+
+
+def attn_fwd(qkv, key_mask, B, S, n_heads, head_dim, out=None, lse=None):
+    out = out if out is not None else torch.empty((B * S, n_heads * head_dim), device=qkv.device, dtype=BF16)
+    lse = lse if lse is not None else torch.empty((B, n_heads, S), device=qkv.device, dtype=torch.float32)
+    check(lib().llark_attn_fwd(_p(qkv), _p(key_mask), _p(out), _p(lse), B, S, n_heads, head_dim,
+                               1.0 / math.sqrt(head_dim), _stream()), "attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None):
+    dqkv = dqkv if dqkv is not None else torch.empty_like(qkv)
+    need = lib().llark_attn_bwd_workspace(B, S, n_heads)
+    if workspace is None:
+        workspace = torch.empty(need, device=qkv.device, dtype=torch.uint8)
+    check(lib().llark_attn_bwd(_p(qkv), _p(key_mask), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, n_heads, head_dim,
+                               1.0 / math.sqrt(head_dim), _p(workspace), _stream()), "attn_bwd")
+    return dqkv
+
+
+def colsum(x, out, accumulate=False):
+    rows, H = x.shape
+    check(lib().llark_colsum(_p(x), _p(out), rows, H, int(accumulate), _stream()), "colsum")
+    return out
+
+
+def ce_fwd(logits, ldv, V, labels, B, S, row_loss, row_lse, loss_out):
+    check(lib().llark_ce_fwd(_p(logits), ldv, V, _p(labels), B, S, _p(row_loss), _p(row_lse), _p(loss_out), _stream()),
+          "ce_fwd")
+
+
+def ce_bwd(logits, ldv, V, labels, B, S, row_lse, loss_out, gscale_ptr, gscale, dlogits):
+    check(lib().llark_ce_bwd(_p(logits), ldv, V, _p(labels), B, S, _p(row_lse), _p(loss_out), _p(gscale_ptr),
+                             float(gscale), _p(dlogits), _stream()), "ce_bwd")
+
+
+def grad_sumsq(g, out, accumulate, workspace):
+    check(lib().llark_grad_sumsq(_p(g), g.numel(), _p(out), int(accumulate), _p(workspace), _stream()), "grad_sumsq")
+
+
+def adamw_step(p, g, m, v, sumsq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0,
+               zero_grad=False):
+    check(lib().llark_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq), lr, beta1, beta2, eps, weight_decay,
+                                 step, grad_scale, max_norm, int(zero_grad), _stream()), "adamw_step")
+
+
+# ------------------------------------------------------------------------------------------------ Jukebox front end
+def jb_conv_down(x, w, b):
+    N, c_in, T = x.shape
+    c_out = w.shape[0]
+    y = torch.empty((N, c_out, T // 2), device=x.device, dtype=torch.float32)
+    check(lib().llark_jb_conv_down(_p(x), _p(w), _p(b), _p(y), N, c_in, c_out, T, _stream()), "jb_conv_down")
+    return y
+
+
+def jb_resblock(x, w1, b1, w2, b2, dilation):
+    N, C, T = x.shape
+    y = torch.empty_like(x)
+    check(lib().llark_jb_resblock(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y), N, T, dilation, _stream()),
+          "jb_resblock")
+    return y
+
+
+def jb_conv_k3(x, w, b):
+    N, c_in, T = x.shape
+    c_out = w.shape[0]
+    y = torch.empty((N, c_out, T), device=x.device, dtype=torch.float32)
+    check(lib().llark_jb_conv_k3(_p(x), _p(w), _p(b), _p(y), N, c_in, c_out, T, _stream()), "jb_conv_k3")
+    return y
+
+
+def jb_vq_encode(x, codebook):
+    N, E, T = x.shape
+    codes = torch.empty((N, T), device=x.device, dtype=torch.int64)
+    check(lib().llark_jb_vq_encode(_p(x), _p(codebook), _p(codes), N, T, codebook.shape[0], _stream()), "jb_vq_encode")
+    return codes
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, out_dtype=torch.float32, out=None):
+    rows, W = x.shape
+    out = out if out is not None else torch.empty((rows, W), device=x.device, dtype=out_dtype)
+    check(lib().llark_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(out), int(out.dtype == BF16), rows, W, eps,
+                                    _stream()), "layernorm_fwd")
+    return out
+
+
+def jb_embed_tokens(codes, emb, y_cond, pos_emb, x_cond):
+    N, T = codes.shape
+    W = emb.shape[1]
+    out = torch.empty((N * T, W), device=codes.device, dtype=torch.float32)
+    check(lib().llark_jb_embed_tokens(_p(codes), _p(emb), _p(y_cond), _p(pos_emb), _p(x_cond), _p(out), N, T, W,
+                                      _stream()), "jb_embed_tokens")
+    return out
+
+
+def jb_sparse_attn(qkv, N, T, heads, dh, block, pattern, out=None):
+    out = out if out is not None else torch.empty((N * T, heads * dh), device=qkv.device, dtype=torch.float32)
+    check(lib().llark_jb_sparse_attn(_p(qkv), _p(out), N, T, heads, dh, block, pattern, _stream()), "jb_sparse_attn")
+    return out
+
+
+def quick_gelu(x, out=None):
+    out = out if out is not None else torch.empty_like(x)
+    check(lib().llark_quick_gelu(_p(x), _p(out), x.numel(), _stream()), "quick_gelu")
+    return out
+
+
+def add3(a, b, c=None, out=None):
+    out = out if out is not None else torch.empty_like(a)
+    check(lib().llark_add3(_p(a), _p(b), _p(c), _p(out), a.numel(), _stream()), "add3")
+    return out
+
+
+def jb_pool(acts, T_valid, frame):
+    W = acts.shape[1]
+    out = torch.empty((T_valid // frame, W), device=acts.device, dtype=torch.float32)
+    check(lib().llark_jb_pool(_p(acts), _p(out), T_valid, W, frame, _stream()), "jb_pool")
+    return out

@@ -1,0 +1,353 @@
+"""GPU parity tests of every C-ABI kernel against a plain PyTorch fp32 restatement of the same op.
+
+These are kernel-level tests (one op at a time, through the C-ABI via llark_b200.ops). The model-level parity
+tests against the oracle / golden fixtures live in test_model_gpu.py.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _ops():
+    from llark_b200 import ops
+
+    return ops
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 256), (256, 512, 4096), (240, 4096, 4800), (512, 1004, 256), (384, 768, 1000),
+    (100, 72, 136), (1024, 4096, 4096),
+]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bf16(M, N, K, a_mn, b_mn):
+    ops = _ops()
+    torch.manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda") * 0.5
+    B = torch.randn(N, K, device="cuda") * 0.5
+    a = A.to(BF16)
+    b = B.to(BF16)
+    ref = a.float() @ b.float().t()
+    a_in = a.t().contiguous() if a_mn else a
+    b_in = b.t().contiguous() if b_mn else b
+    if (a_in.stride(0) % 8) or (b_in.stride(0) % 8):
+        pytest.skip("leading dimension not 16-byte aligned for TMA")
+    out = ops.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn)
+    assert out.shape == (M, N)
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert _rel(out, ref) < 5e-3, (err, scale)
+
+
+def test_gemm_bias_residual_and_fp32_out():
+    ops = _ops()
+    torch.manual_seed(0)
+    M, N, K = 300, 520, 192
+    a = torch.randn(M, K, device="cuda").to(BF16)
+    b = torch.randn(N, K, device="cuda").to(BF16)
+    bias = torch.randn(N, device="cuda").to(BF16)
+    res = torch.randn(M, N, device="cuda").to(BF16)
+    ref = a.float() @ b.float().t() + bias.float() + res.float()
+    out = ops.gemm(a, b, bias=bias, residual=res)
+    assert _rel(out, ref) < 5e-3
+    # accumulate in place (wgrad accumulation): R aliases C
+    acc = res.clone()
+    ops.gemm(a, b, out=acc, residual=acc)
+    assert _rel(acc, a.float() @ b.float().t() + res.float()) < 5e-3
+    out32 = ops.gemm(a, b, out_dtype=torch.float32)
+    assert out32.dtype == torch.float32
+    assert _rel(out32, a.float() @ b.float().t()) < 1e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_tf32(a_mn, b_mn):
+    ops = _ops()
+    torch.manual_seed(1)
+    M, N, K = 256, 1200, 4800
+    a = torch.randn(M, K, device="cuda") * 0.3
+    b = torch.randn(N, K, device="cuda") * 0.3
+    bias = torch.randn(N, device="cuda")
+    ref = a.double() @ b.double().t() + bias.double()
+    a_in = a.t().contiguous() if a_mn else a
+    b_in = b.t().contiguous() if b_mn else b
+    out = ops.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn, bias=bias)
+    assert out.dtype == torch.float32
+    assert _rel(out, ref) < 2e-3
+
+
+def test_gemm_persistent_many_tiles_and_ld():
+    """More tiles than SMs (several waves per CTA), padded leading dimensions, partial N tile."""
+    ops = _ops()
+    torch.manual_seed(2)
+    M, N, K = 2048, 32004, 512
+    ldv = 32064
+    a = (torch.randn(M, K, device="cuda") * 0.2).to(BF16)
+    w = (torch.randn(N, K, device="cuda") * 0.2).to(BF16)
+    out = torch.zeros(M, ldv, device="cuda", dtype=BF16)
+    ops.gemm(a, w, out=out, N=N)
+    ref = a.float() @ w.float().t()
+    assert _rel(out[:, :N], ref) < 5e-3
+    assert out[:, N:].abs().max().item() == 0.0
+    # dgrad through the padded buffer: dH = dlogits[M, V(ld 32064)] @ W[V, K]
+    dl = (torch.randn(M, ldv, device="cuda") * 0.1).to(BF16)
+    dl[:, N:] = float("nan")  # padding must never be read as data (TMA clips at V)
+    dh = ops.gemm(dl, w, b_mn=True, M=M, N=K, K=N, lda=ldv)
+    ref2 = dl[:, :N].float() @ w.float()
+    assert torch.isfinite(dh.float()).all()
+    assert _rel(dh, ref2) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def test_rmsnorm_fwd_bwd():
+    ops = _ops()
+    torch.manual_seed(3)
+    rows, H = 257, 4096
+    x = torch.randn(rows, H, device="cuda").to(BF16)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(BF16)
+    rstd = torch.empty(rows, device="cuda")
+    y = ops.rmsnorm_fwd(x, w, 1e-5, rstd=rstd)
+
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    var = xf.pow(2).mean(-1, keepdim=True)
+    ref = wf * (xf * torch.rsqrt(var + 1e-5))
+    assert _rel(y, ref) < 4e-3
+    dy = torch.randn(rows, H, device="cuda").to(BF16)
+    dres = torch.randn(rows, H, device="cuda").to(BF16)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dw = torch.zeros(H, device="cuda", dtype=BF16)
+    ws = torch.empty(296 * H, device="cuda")
+    ops.rmsnorm_bwd(x, w, dy, rstd, dres, dx, dw, False, ws)
+    assert _rel(dx, xf.grad + dres.float()) < 6e-3
+    assert _rel(dw, wf.grad) < 6e-3
+    ops.rmsnorm_bwd(x, w, dy, rstd, None, dx, dw, True, ws)
+    assert _rel(dx, xf.grad) < 6e-3
+    assert _rel(dw, 2 * wf.grad) < 1e-2
+
+
+def _hf_rope_tables(S, D, theta=10000.0):
+    inv = 1.0 / (theta ** (torch.arange(0, D, 2, device="cuda", dtype=torch.float32) / D))
+    pos = torch.arange(S, device="cuda", dtype=torch.float32)
+    freqs = pos[:, None] * inv[None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(BF16), emb.sin().to(BF16)
+
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def test_rope_fwd_and_inverse():
+    ops = _ops()
+    torch.manual_seed(4)
+    B, S, NH, D = 2, 96, 4, 128
+    qkv = torch.randn(B * S, 3 * NH * D, device="cuda").to(BF16)
+    cos, sin = _hf_rope_tables(S, D)
+    ref = qkv.clone().view(B, S, 3, NH, D)
+    c = cos[None, :, None, :]
+    s = sin[None, :, None, :]
+    for i in (0, 1):
+        t = ref[:, :, i]
+        ref[:, :, i] = (t * c) + (_rotate_half(t) * s)  # bf16 arithmetic exactly as HF does it
+    got = qkv.clone()
+    ops.rope_(got, cos, sin, S, NH, D)
+    assert torch.equal(got.view(B, S, 3, NH, D)[:, :, 2], qkv.view(B, S, 3, NH, D)[:, :, 2])
+    assert (got.float() - ref.view(B * S, -1).float()).abs().max().item() <= 0.04
+    assert _rel(got, ref.view(B * S, -1)) < 3e-3
+    # inverse is the transpose: <rope(x), y> == <x, rope^T(y)>
+    y = torch.randn_like(qkv.float()).to(BF16)
+    yi = y.clone()
+    ops.rope_(yi, cos, sin, S, NH, D, inverse=True)
+    sel = slice(0, 2 * NH * D)
+    lhs = (got.float()[:, sel] * y.float()[:, sel]).sum().item()
+    rhs = (qkv.float()[:, sel] * yi.float()[:, sel]).sum().item()
+    assert abs(lhs - rhs) / (abs(lhs) + 1e-6) < 2e-2
+
+
+def test_swiglu_fwd_bwd():
+    ops = _ops()
+    torch.manual_seed(5)
+    rows, I = 130, 11008
+    gu = torch.randn(rows, 2 * I, device="cuda").to(BF16)
+    act = ops.swiglu_fwd(gu)
+    g = gu[:, :I].float().requires_grad_(True)
+    u = gu[:, I:].float().requires_grad_(True)
+    ref = torch.nn.functional.silu(g) * u
+    assert _rel(act, ref) < 4e-3
+    d = torch.randn(rows, I, device="cuda").to(BF16)
+    ref.backward(d.float())
+    dgu = ops.swiglu_bwd(gu, d)
+    assert _rel(dgu[:, :I], g.grad) < 5e-3
+    assert _rel(dgu[:, I:], u.grad) < 5e-3
+
+
+def _attn_ref(qkv, mask, B, S, NH, D):
+    q, k, v = qkv.float().view(B, S, 3, NH, D).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(D)
+    causal = torch.ones(S, S, device=qkv.device, dtype=torch.bool).tril()
+    allow = causal[None, None]
+    if mask is not None:
+        allow = allow & mask[:, None, None, :].bool()
+    sc = sc.masked_fill(~allow, float("-inf"))
+    p = torch.softmax(sc, dim=-1)
+    o = p @ v
+    return o.permute(0, 2, 1, 3).reshape(B * S, NH * D)
+
+
+@pytest.mark.parametrize("B,S,NH,pad", [(2, 512, 4, False), (2, 200, 2, True), (1, 64, 1, False), (3, 333, 2, True)])
+def test_attention_fwd_bwd(B, S, NH, pad):
+    ops = _ops()
+    torch.manual_seed(6 + S)
+    D = 128
+    qkv = (torch.randn(B * S, 3 * NH * D, device="cuda") * 0.8).to(BF16)
+    mask = None
+    if pad:
+        lens = torch.randint(S // 2, S + 1, (B,), device="cuda")
+        mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None])
+        mask_u8 = mask.to(torch.uint8).contiguous()
+    else:
+        mask_u8 = None
+    out, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
+    qf = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qf, mask, B, S, NH, D)
+    assert _rel(out, ref) < 6e-3
+    dout = torch.randn(B * S, NH * D, device="cuda").to(BF16)
+    if pad:
+        dout = dout * mask.reshape(B * S, 1).to(BF16)  # padded query rows carry no loss gradient
+    ref.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, mask_u8, out, dout, lse, B, S, NH, D)
+    g = qf.grad.view(B, S, 3, NH, D)
+    got = dqkv.float().view(B, S, 3, NH, D)
+    for i, name in enumerate("qkv"):
+        assert _rel(got[:, :, i], g[:, :, i]) < 1.5e-2, name
+
+
+def test_embed_splice_fwd_bwd_and_flags():
+    ops = _ops()
+    torch.manual_seed(7)
+    B, S, H, V, F = 3, 40, 256, 100, 5
+    start_id, end_id, patch_id = 98, 99, 97
+    ids = torch.randint(3, 90, (B, S), device="cuda")
+    pos = [4, 10, -1]
+    for b, p in enumerate(pos):
+        if p >= 0:
+            ids[b, p] = start_id
+            ids[b, p + 1: p + 1 + F] = patch_id
+            ids[b, p + F + 1] = end_id
+    table = torch.randn(V, H, device="cuda").to(BF16)
+    audio = torch.randn(B * F, H, device="cuda").to(BF16)
+    frames = torch.full((B,), F, device="cuda", dtype=torch.int32)
+    audio_off = (torch.arange(B, device="cuda") * F).to(torch.int64)
+    start_pos = torch.empty(B, device="cuda", dtype=torch.int32)
+    flags = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ops.splice_scan(ids, start_id, end_id, frames, start_pos, flags)
+    assert start_pos.tolist() == pos
+    assert flags.item() == 0
+    out = torch.empty(B, S, H, device="cuda", dtype=BF16)
+    ops.embed_splice_fwd(ids, table, audio, audio_off, frames, start_pos, out)
+    ref = table[ids]
+    for b, p in enumerate(pos):
+        if p >= 0:
+            ref[b, p + 1: p + 1 + F] = audio[b * F: (b + 1) * F]
+    assert torch.equal(out, ref)
+    # backward, detach_text path: only marker rows + audio rows
+    dout = torch.randn(B, S, H, device="cuda").to(BF16)
+    daudio = torch.zeros(B * F, H, device="cuda", dtype=BF16)
+    dtable = torch.zeros(V, H, device="cuda", dtype=BF16)
+    ops.embed_splice_bwd(ids, dout, daudio, audio_off, frames, start_pos, dtable, V, True)
+    ref_da = torch.zeros_like(daudio)
+    ref_dt = torch.zeros(V, H, device="cuda")
+    for b, p in enumerate(pos):
+        if p >= 0:
+            ref_da[b * F: (b + 1) * F] = dout[b, p + 1: p + 1 + F]
+            ref_dt[start_id] += dout[b, p].float()
+            ref_dt[end_id] += dout[b, p + F + 1].float()
+    assert torch.equal(daudio, ref_da)
+    nz = dtable.float().abs().sum(-1).nonzero().flatten().tolist()
+    assert nz == [start_id, end_id]
+    assert _rel(dtable, ref_dt) < 1e-2
+    # flag: end token misplaced / counts differ
+    bad = ids.clone()
+    bad[0, pos[0] + F + 1] = 5
+    flags.zero_()
+    ops.splice_scan(bad, start_id, end_id, frames, start_pos, flags)
+    assert flags.item() & 1 and flags.item() & 2
+
+
+def test_ce_fwd_bwd():
+    ops = _ops()
+    torch.manual_seed(8)
+    B, S, V, ldv = 2, 64, 32004, 32064
+    logits = torch.zeros(B * S, ldv, device="cuda", dtype=BF16)
+    logits[:, :V] = (torch.randn(B * S, V, device="cuda") * 2).to(BF16)
+    logits[:, V:] = 77.0  # padding columns must be ignored
+    labels = torch.randint(0, V, (B, S), device="cuda")
+    labels[:, : S // 2] = -100
+    row_loss = torch.empty(B * S, device="cuda")
+    row_lse = torch.empty(B * S, device="cuda")
+    loss_out = torch.empty(2, device="cuda")
+    ops.ce_fwd(logits, ldv, V, labels, B, S, row_loss, row_lse, loss_out)
+    lf = logits[:, :V].float().view(B, S, V).requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1), ignore_index=-100)
+    assert abs(loss_out[0].item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    assert loss_out[1].item() == (labels[:, 1:] != -100).sum().item()
+    ref.backward()
+    dl = torch.empty_like(logits)
+    ops.ce_bwd(logits, ldv, V, labels, B, S, row_lse, loss_out, None, 1.0, dl)
+    assert dl[:, V:].abs().max().item() == 0
+    assert _rel(dl[:, :V].view(B, S, V), lf.grad) < 5e-3
+
+
+def test_adamw_matches_torch_bf16():
+    ops = _ops()
+    torch.manual_seed(9)
+    n = 1 << 16
+    p0 = torch.randn(n, device="cuda").to(BF16)
+    g0 = (torch.randn(n, device="cuda") * 0.01).to(BF16)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, foreach=True)
+    p = p0.clone()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    sumsq = torch.zeros(1, device="cuda")
+    ws = torch.empty(4096, device="cuda")
+    for step in range(1, 4):
+        g = (g0.float() * step).to(BF16)
+        p_ref.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        gg = g.clone()
+        ops.grad_sumsq(gg, sumsq, False, ws)
+        assert abs(sumsq.sqrt().item() - total.item()) < 2e-2 * total.item()
+        ops.adamw_step(p, gg, m, v, sumsq, 5e-5, 0.9, 0.999, 1e-8, 0.0, step, 1.0, 1.0, True)
+        assert gg.abs().max().item() == 0
+    diff = (p.float() - p_ref.detach().float()).abs()
+    ulp = p_ref.detach().float().abs().clamp_min(1e-3) * 2 ** -7
+    assert (diff <= 2 * ulp).float().mean().item() > 0.999
+
+
+def test_cast_and_colsum():
+    ops = _ops()
+    x = torch.randn(1000, 257, device="cuda")
+    b = ops.cast_f32_to_bf16(x)
+    assert torch.equal(b, x.to(BF16))
+    assert torch.equal(ops.cast_bf16_to_f32(b), b.float())
+    xb = torch.randn(300, 4096, device="cuda").to(BF16)
+    out = torch.zeros(4096, device="cuda", dtype=BF16)
+    ops.colsum(xb, out)
+    assert _rel(out, xb.float().sum(0)) < 4e-3
