@@ -33,7 +33,7 @@ int llark_last_cuda_error(void);
  * GEMM core (tcgen05 / TMEM / TMA).  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ R[M,N]), fp32 accumulate.
  *   a_mn_major = 0: A stored [M][lda] (K contiguous);  1: A stored [K][lda] (M contiguous).
  *   b_mn_major = 0: B stored [N][ldb] (K contiguous);  1: B stored [K][ldb] (N contiguous).
- *   in_fp32 = 0: A,B bf16 (kind::f16);  1: A,B fp32 consumed as TF32 (kind::tf32).
+ *   in_fp32 = 0: A,B bf16 (kind::f16);  1: A,B fp32 consumed as TF32 (kind::tf32, K-major operands only).
  *   c_fp32: C (and R) fp32 instead of bf16.  bias: bf16[N] (fp32[N] if bias_fp32) or NULL.  R may alias C.
  *   max_ctas: 0 = one CTA per SM; >0 caps the persistent grid (tests / overlap with a comm stream).
  * Replaces: nn.Linear / addmm at m2t/models/llamav2.py:133 (mm_projector), :224 (LlamaModel q/k/v/o/gate/up/

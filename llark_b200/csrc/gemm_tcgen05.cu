@@ -418,6 +418,9 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return LLARK_EINVAL;
     int rc = ensure_driver();
     if (rc != LLARK_OK) return rc;
+    // TF32 operands are supported K-major only: MN-major 32-bit operands need the SWIZZLE_128B_BASE32B atom
+    // (measured wrong with the plain 128B swizzle). The Jukebox prior keeps its frozen weights pre-transposed.
+    if (in_fp32 && (a_mn_major || b_mn_major)) return LLARK_EINVAL;
     const int eb = in_fp32 ? 4 : 2;
     const int epr = BLOCK_KB / eb;  // K elements per smem row
     const int vec = c_fp32 ? 4 : 8;

@@ -1,0 +1,418 @@
+"""Execution engine of the LLark/Llama training step on B200.
+
+Host-side orchestration only: every FLOP is a C-ABI call (llark_b200.ops -> libllark_b200.so). The engine owns
+
+  * the flat bf16 parameter bucket (all nn.Parameters of the model are re-pointed to views of it, trainable
+    parameters first) and the flat bf16 gradient bucket (`.grad` of every trainable parameter is a view of it):
+    one ncclAllReduce + one fused AdamW kernel cover the whole model, q/k/v and gate/up projections are adjacent
+    so each is ONE fused GEMM without copying weights, and wgrad GEMMs accumulate in place in their epilogue;
+  * the forward/backward schedule of the decoder stack (manual backward: dgrad/wgrad GEMMs read weights and saved
+    activations in place through MN-major UMMA descriptors, no transposes are materialised).
+
+Reference semantics reproduced: pure-bf16 weights/grads, loss = per-rank mean over
+non-ignored shifted tokens computed on bf16 logits, lm_head frozen when requires_grad is False, text-token
+embedding rows detached when `orig_embeds_params` is set (m2t/models/llamav2.py:176-198).
+"""
+import math
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+_ALIGN = 128  # elements (256 B): keeps every view 16-byte aligned for TMA and fused views gap-free
+
+
+class FlatBuckets:
+    """Packs a list of (name, nn.Parameter) into one flat bf16 buffer, trainable parameters first."""
+
+    def __init__(self, named_params, device):
+        self.device = device
+        self.entries = []  # (name, param, offset, numel)
+        train = [(n, p) for n, p in named_params if p.requires_grad]
+        frozen = [(n, p) for n, p in named_params if not p.requires_grad]
+        off = 0
+        for group in (train, frozen):
+            for n, p in group:
+                if p.dtype != BF16:
+                    raise TypeError(
+                        f"{n} is {p.dtype}: llark_b200 runs the reference's pure-bf16 regime (m2t/train.py:101-103); "
+                        "cast the model with .to(torch.bfloat16) first")
+                self.entries.append((n, p, off, p.numel()))
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            if group is train:
+                self.n_train = off
+        self.total = off
+        self.params = torch.empty(self.total, device=device, dtype=BF16)
+        self.params.zero_()
+        self.grads = torch.zeros(max(self.n_train, _ALIGN), device=device, dtype=BF16)
+        self.signature = tuple((n, p.requires_grad, tuple(p.shape)) for n, p, _, _ in self.entries)
+        self.offsets = {n: (o, k) for n, _, o, k in self.entries}
+        for n, p, o, k in self.entries:
+            view = self.params[o:o + k].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self.grads_attached = False
+
+    def is_current(self, named_params):
+        sig = tuple((n, p.requires_grad, tuple(p.shape)) for n, p in named_params)
+        if sorted(sig) != sorted(self.signature):
+            return False
+        base = self.params.data_ptr()
+        for n, p, o, k in self.entries:
+            if p.data_ptr() != base + 2 * o:
+                return False
+        return True
+
+    def pview(self, name, shape=None, span=1):
+        """View of `span` consecutive parameters starting at `name` (fused q|k|v, gate|up)."""
+        o, k = self.offsets[name]
+        if span == 1:
+            t = self.params[o:o + k]
+            return t.view(shape) if shape is not None else t
+        names = [e[0] for e in self.entries]
+        i = names.index(name)
+        tot = 0
+        for j in range(span):
+            oj, kj = self.entries[i + j][2], self.entries[i + j][3]
+            if oj != o + tot:
+                raise RuntimeError(f"parameters after {name} are not contiguous in the flat bucket")
+            tot += kj
+        return self.params[o:o + tot].view(shape)
+
+    def gview(self, name, shape=None, span=1):
+        o, k = self.offsets[name]
+        if o >= self.n_train:
+            return None
+        if span > 1:
+            names = [e[0] for e in self.entries]
+            i = names.index(name)
+            k = sum(self.entries[i + j][3] for j in range(span))
+        t = self.grads[o:o + k]
+        return t.view(shape) if shape is not None else t
+
+    def grads_live(self):
+        """True when every trainable parameter's .grad is still our view (gradient accumulation in progress)."""
+        if not self.grads_attached:
+            return False
+        gbase = self.grads.data_ptr()
+        for n, p, o, k in self.entries:
+            if o >= self.n_train:
+                continue
+            if p.grad is None or p.grad.data_ptr() != gbase + 2 * o:
+                return False
+        return True
+
+    def attach_grads(self):
+        for n, p, o, k in self.entries:
+            if o >= self.n_train:
+                continue
+            p.grad = self.grads[o:o + k].view(p.shape)
+        self.grads_attached = True
+
+
+class _StepFn(torch.autograd.Function):
+    """Autograd anchor: forward runs the whole CUDA forward, backward the whole manual CUDA backward, which writes
+    the flat gradient bucket and attaches `.grad` views (so no per-parameter autograd accumulation kernels)."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine, batch):
+        loss, logits = engine._forward(batch, need_grad=True)
+        ctx.engine = engine
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        ctx.engine._backward(dloss)
+        return None, None, None
+
+
+class LlamaEngine:
+    def __init__(self, causal_lm):
+        self.lm = causal_lm
+        self.cfg = causal_lm.config
+        self.flat = None
+        self._rope = {}
+        self._saved = None
+        self._ws = {}
+        self.flags = None  # device int32[1]: splice validation bits (see llark_splice_scan)
+        self.launches = 0  # kernels launched by the last forward(+backward): bench.py's gpu_launches
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _named(self):
+        return [(n, p) for n, p in self.lm.named_parameters()]
+
+    def ensure_packed(self):
+        named = self._named()
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("llark_b200 has no CPU path: move the model to a CUDA device (B200) first")
+        if self.flat is None or not self.flat.is_current(named):
+            self.flat = FlatBuckets(named, dev)
+        return self.flat
+
+    def _tables(self, S, device):
+        key = (S, device)
+        if key not in self._rope:
+            D = self.cfg.hidden_size // self.cfg.num_attention_heads
+            theta = getattr(self.cfg, "rope_theta", None)
+            if theta is None:
+                theta = (getattr(self.cfg, "rope_parameters", None) or {}).get("rope_theta", 10000.0)
+            # HF LlamaRotaryEmbedding: fp32 cos/sin cast to the activation dtype (one-time setup, not the hot path)
+            inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.int64).to(device=device, dtype=torch.float) / D))
+            pos = torch.arange(S, device=device, dtype=torch.float32)
+            emb = torch.cat((pos[:, None] * inv[None, :],) * 2, dim=-1)
+            self._rope[key] = (emb.cos().to(BF16).contiguous(), emb.sin().to(BF16).contiguous())
+        return self._rope[key]
+
+    def _workspace(self, name, nbytes, device):
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes or t.device != device:
+            t = torch.empty(nbytes, device=device, dtype=torch.uint8)
+            self._ws[name] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------ public entry
+    def run(self, input_ids, attention_mask, labels, audio_encodings):
+        flat = self.ensure_packed()
+        batch = dict(input_ids=input_ids, attention_mask=attention_mask, labels=labels,
+                     audio_encodings=audio_encodings)
+        need_grad = torch.is_grad_enabled() and labels is not None and flat.n_train > 0
+        if need_grad:
+            anchor = flat.entries[0][1]  # first trainable parameter
+            return _StepFn.apply(anchor, self, batch)
+        return self._forward(batch, need_grad=False)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _forward(self, batch, need_grad):
+        cfg, flat = self.cfg, self.flat
+        ids = batch["input_ids"]
+        if ids.dtype != torch.int64:
+            ids = ids.to(torch.int64)
+        ids = ids.contiguous()
+        dev = ids.device
+        B, S = ids.shape
+        H, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        NH = cfg.num_attention_heads
+        D = H // NH
+        V = self.lm.lm_head.weight.shape[0]
+        M = B * S
+        eps = cfg.rms_norm_eps
+        mask = batch["attention_mask"]
+        mask_u8 = None
+        if mask is not None:
+            mask_u8 = mask.to(torch.bool).contiguous().view(torch.uint8)
+        n0 = self.launches = 0
+
+        table = flat.pview("model.embed_tokens.weight", (V, H))
+        x = torch.empty((M, H), device=dev, dtype=BF16)
+        model = self.lm.model
+        aec = model.audio_encoder_config
+        enc = batch["audio_encodings"]
+        saved = {"B": B, "S": S, "ids": ids, "mask": mask_u8, "layers": []}
+        if enc is not None and getattr(cfg, "use_mm_proj", False):
+            if not aec.use_audio_start_end:
+                raise NotImplementedError("audio_encoder_config.use_audio_start_end=False is not implemented.")
+            if isinstance(enc, (list, tuple)):
+                frames_list = [int(e.shape[0]) for e in enc]
+                enc_cat = torch.cat([e.reshape(e.shape[0], -1) for e in enc], dim=0)
+            else:
+                frames_list = [int(enc.shape[1])] * enc.shape[0]
+                enc_cat = enc.reshape(-1, enc.shape[-1])
+            if len(frames_list) != B:
+                raise ValueError("one audio encoding per sample is required")
+            enc_cat = enc_cat.to(dev)
+            if enc_cat.dtype == torch.float32:
+                enc_bf = ops.cast_f32_to_bf16(enc_cat.contiguous())
+                n0 += 1
+            else:
+                enc_bf = enc_cat.to(BF16).contiguous()
+            A = enc_bf.shape[1]
+            Wp = flat.pview("model.mm_projector.weight", (H, A))
+            bp = flat.pview("model.mm_projector.bias", (H,))
+            feats = ops.gemm(enc_bf, Wp, bias=bp)  # [sumF, H]
+            frames = torch.tensor(frames_list, dtype=torch.int32).to(dev, non_blocking=True)
+            offs = [0]
+            for f in frames_list[:-1]:
+                offs.append(offs[-1] + f)
+            audio_off = torch.tensor(offs, dtype=torch.int64).to(dev, non_blocking=True)
+            start_pos = torch.empty(B, device=dev, dtype=torch.int32)
+            if self.flags is None or self.flags.device != dev:
+                self.flags = torch.zeros(1, device=dev, dtype=torch.int32)
+            ops.splice_scan(ids, int(aec.audio_start_token), int(aec.audio_end_token), frames, start_pos, self.flags)
+            ops.embed_splice_fwd(ids, table, feats, audio_off, frames, start_pos, x.view(B, S, H))
+            n0 += 3
+            saved.update(enc_bf=enc_bf, frames=frames, audio_off=audio_off, start_pos=start_pos, n_feat=feats.shape[0])
+        else:
+            ops.embed_splice_fwd(ids, table, None, None, None, None, x.view(B, S, H))
+            n0 += 1
+            saved.update(enc_bf=None, frames=None, audio_off=None, start_pos=None, n_feat=0)
+
+        cos, sin = self._tables(S, dev)
+        for l in range(L):
+            pfx = f"model.layers.{l}."
+            w_in = flat.pview(pfx + "input_layernorm.weight")
+            w_post = flat.pview(pfx + "post_attention_layernorm.weight")
+            Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
+            Wo = flat.pview(pfx + "self_attn.o_proj.weight", (H, H))
+            Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
+            Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
+            rstd1 = torch.empty(M, device=dev, dtype=torch.float32)
+            xn1 = ops.rmsnorm_fwd(x, w_in, eps, rstd=rstd1)
+            qkv = ops.gemm(xn1, Wqkv)
+            ops.rope_(qkv, cos, sin, S, NH, D)
+            attn, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
+            x_mid = ops.gemm(attn, Wo, residual=x)
+            rstd2 = torch.empty(M, device=dev, dtype=torch.float32)
+            xn2 = ops.rmsnorm_fwd(x_mid, w_post, eps, rstd=rstd2)
+            gu = ops.gemm(xn2, Wgu)
+            act = ops.swiglu_fwd(gu)
+            x_out = ops.gemm(act, Wd, residual=x_mid)
+            n0 += 9
+            if need_grad:
+                saved["layers"].append((x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act))
+            x = x_out
+
+        w_norm = flat.pview("model.norm.weight")
+        rstd_f = torch.empty(M, device=dev, dtype=torch.float32)
+        hn = ops.rmsnorm_fwd(x, w_norm, eps, rstd=rstd_f)
+        ldv = (V + 63) // 64 * 64
+        logits_buf = torch.empty((M, ldv), device=dev, dtype=BF16)
+        Wlm = flat.pview("lm_head.weight", (V, H))
+        ops.gemm(hn, Wlm, out=logits_buf, N=V)
+        n0 += 2
+        logits = logits_buf.view(B, S, ldv)[:, :, :V]
+        loss = None
+        labels = batch["labels"]
+        if labels is not None:
+            labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+            row_loss = torch.empty(M, device=dev, dtype=torch.float32)
+            row_lse = torch.empty(M, device=dev, dtype=torch.float32)
+            loss_out = torch.empty(2, device=dev, dtype=torch.float32)
+            ops.ce_fwd(logits_buf, ldv, V, labels, B, S, row_loss, row_lse, loss_out)
+            n0 += 2
+            loss = loss_out[0]
+            if need_grad:
+                saved.update(x_final=x, rstd_f=rstd_f, hn=hn, logits_buf=logits_buf, ldv=ldv, labels=labels,
+                             row_lse=row_lse, loss_out=loss_out)
+        self._saved = saved if need_grad else None
+        self.launches = n0
+        return loss, logits
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _backward(self, dloss):
+        cfg, flat, sv = self.cfg, self.flat, self._saved
+        if sv is None:
+            raise RuntimeError("backward called without a saved forward (double backward is not supported)")
+        self._saved = None
+        B, S = sv["B"], sv["S"]
+        H, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        NH = cfg.num_attention_heads
+        D = H // NH
+        V = self.lm.lm_head.weight.shape[0]
+        M = B * S
+        dev = sv["ids"].device
+        n0 = self.launches
+        acc = flat.grads_live()  # accumulate into existing grads (micro-batches 2..k) or overwrite (first)
+        ws_norm = self._workspace("norm", ops.lib().llark_rmsnorm_bwd_workspace(M, H), dev)
+        ws_attn = self._workspace("attn", ops.lib().llark_attn_bwd_workspace(B, S, NH), dev)
+
+        def wgrad(name, dy, xin, shape, span=1):
+            """dW[N,K] (+)= dy[M,N]^T @ xin[M,K] written straight into the flat gradient bucket."""
+            g = flat.gview(name, shape, span=span)
+            if g is None:
+                return 0
+            ops.gemm(dy, xin, a_mn=True, b_mn=True, out=g, residual=g if acc else None)
+            return 1
+
+        # loss -> dlogits -> d(final hidden)
+        ldv = sv["ldv"]
+        dlogits = torch.empty_like(sv["logits_buf"])
+        dl = dloss.to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        ops.ce_bwd(sv["logits_buf"], ldv, V, sv["labels"], B, S, sv["row_lse"], sv["loss_out"], dl, 1.0, dlogits)
+        Wlm = flat.pview("lm_head.weight", (V, H))
+        dhn = ops.gemm(dlogits, Wlm, b_mn=True, M=M, N=H, K=V, lda=ldv)
+        n0 += 2
+        g_lm = flat.gview("lm_head.weight", (V, H))
+        if g_lm is not None:  # only when lm_head is trainable (the reference freezes it, llamav2.py:412-415)
+            ops.gemm(dlogits, sv["hn"], a_mn=True, b_mn=True, M=V, N=H, K=M, lda=ldv, out=g_lm,
+                     residual=g_lm if acc else None)
+            n0 += 1
+        del dlogits
+        dx = torch.empty((M, H), device=dev, dtype=BF16)
+        g_norm = flat.gview("model.norm.weight")
+        ops.rmsnorm_bwd(sv["x_final"], flat.pview("model.norm.weight"), dhn, sv["rstd_f"], None, dx, g_norm, acc,
+                        ws_norm)
+        n0 += 2
+        cos, sin = self._tables(S, dev)
+
+        for l in reversed(range(L)):
+            pfx = f"model.layers.{l}."
+            x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act = sv["layers"][l]
+            sv["layers"][l] = None
+            Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
+            Wo = flat.pview(pfx + "self_attn.o_proj.weight", (H, H))
+            Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
+            Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
+            # MLP
+            dact = ops.gemm(dx, Wd, b_mn=True)  # [M,I] = dx[M,H] @ Wd[H,I]
+            n0 += 1 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
+            dgu = ops.swiglu_bwd(gu, dact)
+            del dact
+            dxn2 = ops.gemm(dgu, Wgu, b_mn=True)  # [M,H] = dgu[M,2I] @ Wgu[2I,H]
+            n0 += 2 + wgrad(pfx + "mlp.gate_proj.weight", dgu, xn2, (2 * I, H), span=2)
+            del dgu
+            dx_mid = torch.empty((M, H), device=dev, dtype=BF16)
+            ops.rmsnorm_bwd(x_mid, flat.pview(pfx + "post_attention_layernorm.weight"), dxn2, rstd2, dx, dx_mid,
+                            flat.gview(pfx + "post_attention_layernorm.weight"), acc, ws_norm)
+            # attention
+            dattn = ops.gemm(dx_mid, Wo, b_mn=True)
+            n0 += 3 + wgrad(pfx + "self_attn.o_proj.weight", dx_mid, attn, (H, H))
+            dqkv = ops.attn_bwd(qkv, sv["mask"], attn, dattn, lse, B, S, NH, D, workspace=ws_attn)
+            ops.rope_(dqkv, cos, sin, S, NH, D, inverse=True)
+            dxn1 = ops.gemm(dqkv, Wqkv, b_mn=True)
+            n0 += 5 + wgrad(pfx + "self_attn.q_proj.weight", dqkv, xn1, (3 * H, H), span=3)
+            ops.rmsnorm_bwd(x, flat.pview(pfx + "input_layernorm.weight"), dxn1, rstd1, dx_mid, dx,
+                            flat.gview(pfx + "input_layernorm.weight"), acc, ws_norm)
+            n0 += 2
+
+        # splice + projector
+        g_table = flat.gview("model.embed_tokens.weight", (V, H))
+        detach_text = getattr(self.lm.model, "orig_embeds_params", None) is not None
+        if not acc:  # overwrite mode: buckets that are scatter-accumulated or may see no work start from zero
+            if g_table is not None:
+                g_table.zero_()
+            if sv["n_feat"] == 0:
+                for nm in ("model.mm_projector.weight", "model.mm_projector.bias"):
+                    if nm in flat.offsets and flat.gview(nm) is not None:
+                        flat.gview(nm).zero_()
+        n_feat = sv["n_feat"]
+        daudio = torch.empty((max(n_feat, 1), H), device=dev, dtype=BF16) if n_feat else None
+        ops.embed_splice_bwd(sv["ids"], dx.view(B, S, H), daudio, sv["audio_off"], sv["frames"], sv["start_pos"],
+                             g_table, V, detach_text)
+        n0 += 1
+        if n_feat:
+            A = sv["enc_bf"].shape[1]
+            n0 += wgrad("model.mm_projector.weight", daudio, sv["enc_bf"], (H, A))
+            g_b = flat.gview("model.mm_projector.bias")
+            if g_b is not None:
+                ops.colsum(daudio, g_b, accumulate=acc)
+                n0 += 1
+        flat.attach_grads()
+        self.launches = n0
+
+    # ------------------------------------------------------------------------------------------ validation
+    def check_flags(self):
+        """Raise the reference's ValueErrors (llamav2.py:146-152, :169-175) from the device flag word (one sync)."""
+        if self.flags is None:
+            return
+        f = int(self.flags.item())
+        if f:
+            self.flags.zero_()
+        if f & 1:
+            raise ValueError("The number of image start tokens and image end tokens should be the same.")
+        if f & 2:
+            raise ValueError("The image end token should follow the image start token.")
+        if f & 4:
+            raise ValueError("llark_b200 supports one audio segment per sample (the reference keeps only the last).")

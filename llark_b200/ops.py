@@ -13,6 +13,10 @@ from ._lib import check, lib
 
 BF16 = torch.bfloat16
 
+# bench.py sets this to a list: every gemm() launch then appends (start_event, end_event, flops) recorded on the
+# launching stream, which is how the roofline of the dominant kernel is measured live inside the timed region.
+GEMM_PROFILE = None
+
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -60,9 +64,17 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_
     else:
         ldr = 0
     bias_fp32 = bias is not None and bias.dtype == torch.float32
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = lib().llark_gemm(_p(a), int(a_mn), lda, _p(b), int(b_mn), ldb, _p(out), ldc, int(c_fp32), _p(bias),
                           int(bias_fp32), _p(residual), ldr, M, N, K, int(in_fp32), max_ctas, _stream())
     check(rc, f"llark_gemm(M={M},N={N},K={K})")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K))
     return out
 
 

@@ -26,7 +26,7 @@ def _rel(a, b):
 
 # ------------------------------------------------------------------------------------------------ GEMM
 GEMM_SHAPES = [
-    (128, 256, 64), (128, 256, 256), (256, 512, 4096), (240, 4096, 4800), (512, 1004, 256), (384, 768, 1000),
+    (128, 256, 64), (128, 256, 256), (256, 512, 4096), (240, 4096, 4800), (512, 1000, 256), (384, 768, 1000),
     (100, 72, 136), (1024, 4096, 4096),
 ]
 
@@ -72,7 +72,16 @@ def test_gemm_bias_residual_and_fp32_out():
     assert _rel(out32, a.float() @ b.float().t()) < 1e-5
 
 
-@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_tf32_mn_major_rejected():
+    ops = _ops()
+    from llark_b200._lib import LlarkError
+
+    a = torch.randn(256, 128, device="cuda")
+    with pytest.raises(LlarkError):
+        ops.gemm(a, a.clone(), b_mn=True)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False)])
 def test_gemm_tf32(a_mn, b_mn):
     ops = _ops()
     torch.manual_seed(1)
