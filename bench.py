@@ -155,15 +155,22 @@ def cpu_slice_seconds(n_layers, threads):
     return time.perf_counter() - t0
 
 
+_CPU_WARM = False
+
+
 def cpu_baseline_value(threads):
-    """Bounded sample: 1-layer and 2-layer slices; full-model time = t1 + 31 * (t2 - t1) (extrapolated)."""
+    """Bounded sample: 1-layer and 3-layer slices; full-model time = t1 + 31 * (t3 - t1) / 2 (extrapolated)."""
+    global _CPU_WARM
+    if not _CPU_WARM:
+        cpu_slice_seconds(1, threads)  # untimed: thread pool, allocator and oneDNN primitive caches
+        _CPU_WARM = True
     t1 = cpu_slice_seconds(1, threads)
-    t2 = cpu_slice_seconds(2, threads)
-    per_layer = max(t2 - t1, 1e-6)
+    t3 = cpu_slice_seconds(3, threads)
+    per_layer = max((t3 - t1) / 2.0, 1e-3)
     full = t1 + 31 * per_layer
-    sample = (f"oracle (PyTorch CPU bf16) fwd+bwd of 1 sample S=512 through 1- and 2-layer slices of Llama-2-7B dims "
-              f"incl. projector/lm_head/CE: t1={t1:.2f}s t2={t2:.2f}s -> 32 layers extrapolated {full:.1f}s/sample; "
-              f"optimizer not included")
+    sample = (f"oracle (PyTorch CPU bf16, {threads} threads) fwd+bwd of 1 sample S=512 through 1- and 3-layer slices "
+              f"of Llama-2-7B dims incl. projector/lm_head/CE: t1={t1:.2f}s t3={t3:.2f}s -> 32 layers extrapolated "
+              f"{full:.1f}s/sample; optimizer step not included")
     return 1.0 / full, sample
 
 

@@ -1,0 +1,276 @@
+"""Host-side mirror of the index / tokenizer work of m2t/data_modules.py: same
+function names, argument meaning and quirks (bit-exact parity is required and tested against golden vectors
+produced by the reference's own functions, tests/golden/data_ref.pt).
+
+What is mirrored (reference file:line):
+    DEFAULT_CONVERSATION_HEADER               data_modules.py:46 + llava/conversation.py:237-271,390 (conv_v1_2)
+    _tokenize_fn                              :57-78
+    _mask_targets                             :81-89   (first two tokens of a human turn stay unmasked, offsets come
+                                                        from separately tokenised segments -- Appendix D.4)
+    sentences_to_formatted_conversation       :92-109  (mutates sentence["value"] in place, as the reference does)
+    preprocess_encodings                      :180-186
+    DataCollatorForSupervisedDataset          :189-222 (bool attention_mask; list of encodings when ragged)
+    _get_audio_token_len                      :225-231
+    preprocess_multimodal_mappable            :234-258
+    preprocess_for_lm_mappable                :261-284
+    concat_audio_token_and_prompt             :287-292
+    webdataset_element_to_conversation        :295-340
+    make_mm_config / make_data_module         :671-717
+The webdataset / GCS reader (:466-520) is replaced by `TarShardDataset`, a plain tarfile reader of the same
+on-disk format (`<key>.audio_encoding.pyd` pickle + `<key>.json`), sharded by rank like wds.split_by_node.
+"""
+import copy
+import io
+import json
+import logging
+import pickle
+import random
+import tarfile
+from dataclasses import dataclass
+from functools import partial
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from llark_b200.special_tokens import (DEFAULT_AUDIO_END_TOKEN, DEFAULT_AUDIO_PATCH_TOKEN, DEFAULT_AUDIO_START_TOKEN,
+                                       DEFAULT_AUDIO_TOKEN, IGNORE_INDEX)
+
+# conv_v1_2 of the reference's m2t/llava/conversation.py: only .system, .roles and .sep are used on this path.
+CONVERSATION_SYSTEM = ("A chat between a curious human and an artificial intelligence assistant. "
+                       "The assistant gives helpful, detailed, and polite answers to the human's questions.")
+CONVERSATION_ROLES = ("Human", "Assistant")
+CONVERSATION_SEP = "###"
+DEFAULT_CONVERSATION_HEADER = f"{CONVERSATION_SYSTEM}\n\n"
+
+
+def _tokenize_fn(strings: Sequence[str], tokenizer) -> Dict:
+    """Tokenize a list of strings one by one (each gets its own BOS); lengths exclude padding."""
+    tokenized_list = [
+        tokenizer(text, return_tensors="pt", padding="longest", max_length=tokenizer.model_max_length,
+                  truncation=True)
+        for text in strings
+    ]
+    input_ids = labels = [t.input_ids[0] for t in tokenized_list]
+    input_ids_lens = labels_lens = [t.input_ids.ne(tokenizer.pad_token_id).sum().item() for t in tokenized_list]
+    return dict(input_ids=input_ids, labels=labels, input_ids_lens=input_ids_lens, labels_lens=labels_lens)
+
+
+def _mask_targets(target, tokenized_lens, speakers):
+    """Mask (in place) the header and every human turn except its first two tokens. Turn k starts at the sum of
+    the separately-tokenised lengths before it (each of those carries its own BOS: the reference's off-by-BOS
+    quirk is preserved on purpose)."""
+    from itertools import accumulate
+
+    starts = list(accumulate(tokenized_lens))  # starts[k] = offset of turn k (after the header)
+    target[: starts[0]] = IGNORE_INDEX
+    for begin, length, who in zip(starts, tokenized_lens[1:], speakers):
+        if who == "human":
+            target[begin + 2: begin + length] = IGNORE_INDEX
+
+
+_ROLE_OF = {"human": CONVERSATION_ROLES[0], "gpt": CONVERSATION_ROLES[1]}
+
+
+def sentences_to_formatted_conversation(header, source, get_conversation=True) -> str:
+    """header + "### <Role>: <text>\n" per turn + trailing "### ". Each turn's "value" is REWRITTEN in place with
+    its formatted form, exactly as the reference does (later code tokenises those rewritten values)."""
+    pieces = [header]
+    for turn in source:
+        role = _ROLE_OF.get(turn["from"].lower(), "unknown")
+        turn["value"] = f"### {role}: {turn['value']}\n"
+        if get_conversation:
+            pieces.append(turn["value"])
+    pieces.append("### ")
+    return "".join(pieces)
+
+
+def preprocess_encodings(audio_encoding, audio_encoding_shape: List[int]) -> torch.Tensor:
+    encoding = torch.Tensor(audio_encoding)
+    encoding = encoding.reshape(audio_encoding_shape)
+    if encoding.ndim == 3:
+        encoding = torch.squeeze(encoding, 0)
+    return encoding
+
+
+@dataclass
+class DataCollatorForSupervisedDataset(object):
+    """Right-pad ids with pad_token_id and labels with -100; bool attention_mask; stack encodings if same shape."""
+
+    tokenizer: Any
+
+    def __call__(self, instances: Sequence[Dict]) -> Dict[str, torch.Tensor]:
+        pad_id = self.tokenizer.pad_token_id
+        width = max(int(inst["input_ids"].shape[0]) for inst in instances)
+        n = len(instances)
+        input_ids = torch.full((n, width), pad_id, dtype=instances[0]["input_ids"].dtype)
+        labels = torch.full((n, width), IGNORE_INDEX, dtype=instances[0]["labels"].dtype)
+        for row, inst in enumerate(instances):
+            k = inst["input_ids"].shape[0]
+            input_ids[row, :k] = inst["input_ids"]
+            labels[row, : inst["labels"].shape[0]] = inst["labels"]
+        batch = dict(input_ids=input_ids, labels=labels, attention_mask=input_ids.ne(pad_id))
+        if "audio_encoding" not in instances[0]:
+            logging.warning("key `audio_encoding` not detected in data collator inputs.")
+            return batch
+        encodings = [inst["audio_encoding"] for inst in instances]
+        same = all(x is not None and x.shape == encodings[0].shape for x in encodings)
+        batch["audio_encodings"] = torch.stack(encodings) if same else encodings
+        return batch
+
+
+def _get_audio_token_len(enc_shape: List[int]) -> int:
+    if len(enc_shape) == 3 and enc_shape[0] == 1:
+        return enc_shape[1]
+    return enc_shape[0]
+
+
+def preprocess_multimodal_mappable(e: Dict[str, Any], multimodal_cfg: Dict[str, Any]):
+    assert not multimodal_cfg["sep_audio_conv_front"], \
+        "need to implement logic for this; see datasets.preprocess_multimodal()."
+    audio_token_len = _get_audio_token_len(e["audio_encoding_shape"])
+    replace_token = DEFAULT_AUDIO_PATCH_TOKEN * audio_token_len
+    if multimodal_cfg["use_audio_start_end"]:
+        replace_token = DEFAULT_AUDIO_START_TOKEN + replace_token + DEFAULT_AUDIO_END_TOKEN
+    out = []
+    for sentence in e["conversations"]:
+        conv = copy.deepcopy(sentence)
+        conv["value"] = sentence["value"].replace(DEFAULT_AUDIO_TOKEN, replace_token)
+        out.append(conv)
+    e["conversations"] = out
+    return e
+
+
+def preprocess_for_lm_mappable(e: Dict[str, Any], tokenizer, header: str = DEFAULT_CONVERSATION_HEADER):
+    source = e["conversations"]
+    conversation = sentences_to_formatted_conversation(header, source)
+    input_ids = _tokenize_fn([conversation], tokenizer)["input_ids"][0]
+    target = copy.deepcopy(input_ids)
+    tokenized_lens = _tokenize_fn([header] + [s["value"] for s in source], tokenizer)["input_ids_lens"]
+    speakers = [sentence["from"] for sentence in source]
+    _mask_targets(target, tokenized_lens, speakers)
+    audio_encoding = preprocess_encodings(e["audio_encoding"], e["audio_encoding_shape"])
+    return dict(input_ids=input_ids, labels=target, audio_encoding=audio_encoding, example_id=e["id"])
+
+
+def concat_audio_token_and_prompt(prompt: str, audio_first: bool) -> str:
+    if audio_first:
+        return "\n".join(("<audio>", prompt))
+    return "\n".join((prompt, "<audio>"))
+
+
+def webdataset_element_to_conversation(src):
+    """One (json.response[], audio_encoding.pyd) element -> one dict per question/answer pair; the audio token is
+    placed before or after the question by a coin flip of Python's `random` (seed it in tests, Appendix D.6)."""
+    for elem in src:
+        if "json" not in elem or not elem["json"].get("response"):
+            logging.warning(f"no valid json response for {elem['__key__']}; skipping")
+            continue
+        if not isinstance(elem["json"]["response"], list):
+            logging.warning(f"invalid response for {elem['__key__']} (could be empty); skipping")
+            continue
+        try:
+            audio_encoding = elem["audio_encoding.pyd"]
+            audio_encoding_shape = list(audio_encoding.shape)
+        except AttributeError:
+            logging.warning(f"error reading encoding for {elem['__key__']}, potentially the file is corrupted; "
+                            "skipping")
+            continue
+        for response in elem["json"]["response"]:
+            question, answer = (response["question"], response["answer"])
+            audio_first = random.uniform(0.0, 1.0) > 0.5
+            prompt_text = concat_audio_token_and_prompt(question, audio_first)
+            yield {"audio_encoding": audio_encoding, "audio_encoding_shape": audio_encoding_shape,
+                   "id": elem["__key__"],
+                   "conversations": [{"from": "human", "value": prompt_text}, {"from": "gpt", "value": answer}]}
+
+
+class TarShardDataset(torch.utils.data.IterableDataset):
+    """Reader of the reference's webdataset shards with the standard library only: consecutive tar members
+    `<key>.audio_encoding.pyd` (pickled array/tensor) and `<key>.json` form one element. Shards are split across
+    ranks (wds.split_by_node) and dataloader workers; corrupt members are skipped with a warning
+    (wds.warn_and_continue)."""
+
+    def __init__(self, urls, multimodal_cfg, tokenizer, is_train, rank=0, world=1, seed=0):
+        self.urls = list(urls)
+        self.cfg, self.tokenizer, self.is_train = multimodal_cfg, tokenizer, is_train
+        self.rank, self.world, self.seed = rank, world, seed
+
+    def _elements(self, path):
+        cur_key, cur = None, {}
+        with tarfile.open(path) as tf:
+            for m in tf:
+                if not m.isfile():
+                    continue
+                key, _, ext = m.name.partition(".")
+                if key != cur_key and cur:
+                    yield cur
+                    cur = {}
+                cur_key = key
+                cur["__key__"] = key
+                try:
+                    data = tf.extractfile(m).read()
+                    if ext == "json":
+                        cur["json"] = json.loads(data)
+                    elif ext.endswith("pyd"):
+                        cur[ext] = pickle.load(io.BytesIO(data))
+                except Exception as e:  # noqa: BLE001
+                    logging.warning(f"skipping corrupt member {m.name}: {e!r}")
+            if cur:
+                yield cur
+
+    def __iter__(self):
+        info = torch.utils.data.get_worker_info()
+        wid, nw = (info.id, info.num_workers) if info else (0, 1)
+        shards = self.urls[self.rank::self.world][wid::nw]
+        rng = random.Random(self.seed + 1000 * self.rank + wid)
+        mm = partial(preprocess_multimodal_mappable, multimodal_cfg=self.cfg)
+        lm = partial(preprocess_for_lm_mappable, tokenizer=self.tokenizer)
+        while True:
+            order = list(shards)
+            if self.is_train:
+                rng.shuffle(order)
+            for path in order:
+                for e in webdataset_element_to_conversation(self._elements(path)):
+                    yield lm(mm(e))
+            if not self.is_train:
+                return
+
+
+def expand_url_to_file_list(url: str) -> List[str]:
+    """Comma-separated list with {a..b} brace ranges (the subset of braceexpand the reference's paths use)."""
+    import re
+
+    out = []
+    for part in url.split(","):
+        m = re.search(r"\{(\d+)\.\.(\d+)\}", part)
+        if not m:
+            out.append(part)
+            continue
+        a, b = m.group(1), m.group(2)
+        width = len(a) if a.startswith("0") else 0
+        for i in range(int(a), int(b) + 1):
+            out.append(part[: m.start()] + str(i).zfill(width) + part[m.end():])
+    return out
+
+
+def make_mm_config(data_args):
+    return dict(is_multimodal=data_args.is_multimodal, sep_audio_conv_front=data_args.sep_audio_conv_front,
+                audio_folder=data_args.audio_folder,
+                use_audio_start_end=getattr(data_args, "mm_use_audio_start_end", False),
+                audio_processor=getattr(data_args, "audio_encoding_processor", None))
+
+
+def make_data_module(tokenizer, data_args, data_collator_cls=DataCollatorForSupervisedDataset) -> Dict:
+    """Dataset + collator for supervised fine-tuning (m2t/data_modules.py:681-717)."""
+    import os
+
+    multimodal_cfg = make_mm_config(data_args)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    train_dataset = eval_dataset = None
+    if data_args.train_data_path:
+        train_dataset = TarShardDataset(expand_url_to_file_list(data_args.train_data_path), multimodal_cfg, tokenizer,
+                                        True, rank, world)
+    if data_args.eval_data_path:
+        eval_dataset = TarShardDataset(expand_url_to_file_list(data_args.eval_data_path), multimodal_cfg, tokenizer,
+                                       False, rank, world)
+    return dict(train_dataset=train_dataset, eval_dataset=eval_dataset, data_collator=data_collator_cls(tokenizer=tokenizer))

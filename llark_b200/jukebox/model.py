@@ -1,0 +1,213 @@
+"""B200-native Jukebox "5b" front-end modules: the objects that jukebox/main.py receives from
+`jukebox.make_models.make_vqvae / make_prior` in the reference (jukebox/main.py:176-200), re-implemented on the
+C-ABI kernels (conv stack, VQ, LayerNorm, factored attention, tcgen05 GEMMs, pool).
+
+Only what the reference's call sites touch is provided:
+    vqvae.encode(x[N,T,1]) -> list of code tensors, last = top level                (jukebox/main.py:61-63)
+    top_prior.raw_to_tokens, .labeller.get_batch_labels, .get_y, .get_cond           (jukebox/main.py:74-93)
+    top_prior.prior.only_encode, top_prior.prior.forward(x, x_cond=, y_cond=, encoder_kv=None, fp16=False)
+                                                                                      (jukebox/main.py:101-110)
+Architecture: SURVEY Appendix A (openai/jukebox@08efbbc, not vendored). Levels 0/1 of the VQ-VAE are dead work
+in the reference (only zs[-1] is kept, :63) and are skipped: results are identical.
+
+Weights: no checkpoint exists offline; `state` dicts use the names of oracle/jukebox_oracle.py so parity tests can
+load identical parameters. Conv1D weights of the prior are stored TRANSPOSED ([n_out, n_in], K-major) once at
+load, so every GEMM reads its operands K-major (TF32 UMMA supports K-major only).
+"""
+import math
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import torch
+
+from llark_b200 import ops
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class JukeboxConfig:
+    sample_length: int = 1048576
+    downs_t: tuple = (3, 2, 2)
+    width: int = 32
+    depth: int = 4
+    emb_width: int = 64
+    l_bins: int = 2048
+    dilation_growth_rate: int = 3
+    n_ctx: int = 8192
+    prior_width: int = 4800
+    prior_depth: int = 36
+    heads: int = 8
+    m_attn: float = 0.25
+    m_mlp: float = 1.0
+    blocks: int = 128
+    ln_eps: float = 1e-5
+
+    @property
+    def hop(self):
+        return 2 ** sum(self.downs_t)
+
+    @property
+    def attn_width(self):
+        return int(self.m_attn * self.prior_width)
+
+    @property
+    def mlp_width(self):
+        return int(self.m_mlp * self.prior_width)
+
+    @property
+    def block_ctx(self):
+        return self.n_ctx // self.blocks
+
+
+def random_vqvae_state(cfg, seed=0, device="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    st = {}
+    c_in = 1
+    for b, down_t in enumerate(cfg.downs_t):
+        for i in range(down_t):
+            cin = c_in if i == 0 else cfg.width
+            st[f"enc.{b}.down.{i}.w"] = torch.randn(cfg.width, cin, 4, generator=g) / math.sqrt(cin * 4)
+            st[f"enc.{b}.down.{i}.b"] = torch.randn(cfg.width, generator=g) * 0.02
+            for d in range(cfg.depth):
+                st[f"enc.{b}.res.{i}.{d}.w1"] = torch.randn(cfg.width, cfg.width, 3, generator=g) / math.sqrt(cfg.width * 3)
+                st[f"enc.{b}.res.{i}.{d}.b1"] = torch.randn(cfg.width, generator=g) * 0.02
+                st[f"enc.{b}.res.{i}.{d}.w2"] = torch.randn(cfg.width, cfg.width, 1, generator=g) / math.sqrt(cfg.width)
+                st[f"enc.{b}.res.{i}.{d}.b2"] = torch.randn(cfg.width, generator=g) * 0.02
+        st[f"enc.{b}.proj.w"] = torch.randn(cfg.emb_width, cfg.width, 3, generator=g) / math.sqrt(cfg.width * 3)
+        st[f"enc.{b}.proj.b"] = torch.randn(cfg.emb_width, generator=g) * 0.02
+        c_in = cfg.emb_width
+    st["codebook"] = torch.randn(cfg.l_bins, cfg.emb_width, generator=g)
+    return st
+
+
+class JukeboxVQVAE:
+    """Top-level (level 2) encoder + bottleneck of the Jukebox VQ-VAE."""
+
+    def __init__(self, cfg, state, device="cuda"):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.w = {k: v.to(self.device, torch.float32).contiguous() for k, v in state.items()}
+        self.sample_length = cfg.sample_length
+
+    def encode_top_latents(self, x):
+        """x fp32 [N,1,T] -> fp32 [N,64,T/128] (time-tiled fused res-blocks, one HBM pass per block)."""
+        cfg, w = self.cfg, self.w
+        h = x
+        for b, down_t in enumerate(cfg.downs_t):
+            for i in range(down_t):
+                h = ops.jb_conv_down(h, w[f"enc.{b}.down.{i}.w"], w[f"enc.{b}.down.{i}.b"])
+                for d in range(cfg.depth):
+                    h = ops.jb_resblock(h, w[f"enc.{b}.res.{i}.{d}.w1"], w[f"enc.{b}.res.{i}.{d}.b1"],
+                                        w[f"enc.{b}.res.{i}.{d}.w2"], w[f"enc.{b}.res.{i}.{d}.b2"],
+                                        cfg.dilation_growth_rate ** d)
+            h = ops.jb_conv_k3(h, w[f"enc.{b}.proj.w"], w[f"enc.{b}.proj.b"])
+        return h
+
+    def encode(self, x):
+        """Reference call: vqvae.encode(FloatTensor[N,T,1]) -> zs (list, last = top level) (jukebox/main.py:61)."""
+        if x.dim() != 3 or x.shape[-1] != 1:
+            raise AssertionError(f"expected [N, T, 1] audio, got {tuple(x.shape)}")
+        x = x.to(self.device, torch.float32).permute(0, 2, 1).contiguous()  # NTC -> NCT
+        z = ops.jb_vq_encode(self.encode_top_latents(x), self.w["codebook"])
+        return [None, None, z]
+
+
+def random_prior_state(cfg, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    W, A, Mw = cfg.prior_width, cfg.attn_width, cfg.mlp_width
+    st = {"x_emb": torch.randn(cfg.l_bins, W, generator=g) * 0.02,
+          "pos_emb": torch.randn(cfg.n_ctx, W, generator=g) * 0.01,
+          "x_cond": torch.randn(cfg.n_ctx, W, generator=g) * 0.01,
+          "y_cond": torch.randn(W, generator=g) * 0.02}
+    for d in range(cfg.prior_depth):
+        q = f"blk.{d}."
+        st[q + "ln0.g"] = 1 + 0.1 * torch.randn(W, generator=g)
+        st[q + "ln0.b"] = 0.02 * torch.randn(W, generator=g)
+        st[q + "c_attn.w"] = torch.randn(W, 3 * A, generator=g) * (0.7 / math.sqrt(W))
+        st[q + "c_attn.b"] = 0.02 * torch.randn(3 * A, generator=g)
+        st[q + "c_proj.w"] = torch.randn(A, W, generator=g) * (0.3 / math.sqrt(A))
+        st[q + "c_proj.b"] = 0.02 * torch.randn(W, generator=g)
+        st[q + "ln1.g"] = 1 + 0.1 * torch.randn(W, generator=g)
+        st[q + "ln1.b"] = 0.02 * torch.randn(W, generator=g)
+        st[q + "fc.w"] = torch.randn(W, Mw, generator=g) * (0.7 / math.sqrt(W))
+        st[q + "fc.b"] = 0.02 * torch.randn(Mw, generator=g)
+        st[q + "fc_proj.w"] = torch.randn(Mw, W, generator=g) * (0.3 / math.sqrt(Mw))
+        st[q + "fc_proj.b"] = 0.02 * torch.randn(W, generator=g)
+    return st
+
+
+class PriorTransformer:
+    """`top_prior.prior`: ConditionalAutoregressive2D restricted to what LLark calls (only_encode forward)."""
+
+    def __init__(self, cfg, state, device="cuda", precision="tf32"):
+        if precision not in ("tf32", "bf16"):
+            raise ValueError("precision must be 'tf32' (parity mode: fp32 storage, TF32 tensor cores) or 'bf16'")
+        self.cfg, self.device, self.precision = cfg, torch.device(device), precision
+        self.only_encode = False
+        wdt = torch.float32 if precision == "tf32" else BF16
+        self.w = {}
+        for k, v in state.items():
+            v = v.to(self.device, torch.float32)
+            if k.endswith((".c_attn.w", ".c_proj.w", ".fc.w", ".fc_proj.w")):
+                v = v.t().contiguous().to(wdt)  # Conv1D [n_in, n_out] -> K-major [n_out, n_in]
+            self.w[k] = v.contiguous()
+
+    def _lin(self, x, name, residual=None):
+        return ops.gemm(x, self.w[name + ".w"], bias=self.w[name + ".b"], residual=residual,
+                        out_dtype=torch.float32)
+
+    def forward(self, x, x_cond=None, y_cond=None, encoder_kv=None, fp16=False):
+        """codes int64 [N,T] -> activations fp32 [N,T,W] (reference: jukebox/main.py:108; fp16 must be False)."""
+        if not self.only_encode:
+            raise NotImplementedError("only the only_encode=True activation path is part of LLark's hot path")
+        if fp16 or encoder_kv is not None:
+            raise NotImplementedError("LLark calls the prior with encoder_kv=None, fp16=False")
+        cfg, w = self.cfg, self.w
+        N, T = x.shape
+        xc = (x_cond if x_cond is not None else w["x_cond"]).reshape(-1, cfg.prior_width)[:T].contiguous().float()
+        yc = (y_cond if y_cond is not None else w["y_cond"]).reshape(-1)[: cfg.prior_width].contiguous().float()
+        h = ops.jb_embed_tokens(x.to(self.device).contiguous(), w["x_emb"], yc, w["pos_emb"], xc)  # [N*T, W]
+        act_dt = torch.float32 if self.precision == "tf32" else BF16
+        dh = cfg.attn_width // cfg.heads
+        bc = T // cfg.blocks if cfg.blocks <= T else T
+        for d in range(cfg.prior_depth):
+            q = f"blk.{d}"
+            n0 = ops.layernorm_fwd(h, w[q + ".ln0.g"], w[q + ".ln0.b"], cfg.ln_eps, out_dtype=act_dt)
+            qkv = self._lin(n0, q + ".c_attn")
+            a = ops.jb_sparse_attn(qkv, N, T, cfg.heads, dh, bc, d % 3)
+            if act_dt == BF16:
+                a = ops.cast_f32_to_bf16(a)
+            xa = self._lin(a, q + ".c_proj", residual=h)  # x + a
+            n1 = ops.layernorm_fwd(xa, w[q + ".ln1.g"], w[q + ".ln1.b"], cfg.ln_eps, out_dtype=act_dt)
+            m = ops.quick_gelu(self._lin(n1, q + ".fc"))
+            if act_dt == BF16:
+                m = ops.cast_f32_to_bf16(m)
+            h = self._lin(m, q + ".fc_proj", residual=xa)  # (x + a) + m
+        return h.view(N, T, cfg.prior_width)
+
+
+class _Labeller:
+    def get_batch_labels(self, metas, device="cuda"):
+        """The reference builds artist/genre/timing label tensors here; for the fixed "unknown" metas of
+        jukebox/main.py:81-89 they select constant conditioning rows, carried by the prior state."""
+        return SimpleNamespace(metas=metas, n=len(metas))
+
+
+class JukeboxTopPrior:
+    def __init__(self, cfg, state, device="cuda", precision="tf32"):
+        self.cfg = cfg
+        self.raw_to_tokens = cfg.hop
+        self.prior = PriorTransformer(cfg, state, device, precision)
+        self.labeller = _Labeller()
+
+    def get_y(self, labels, start):
+        return labels
+
+    def get_cond(self, z_conds, y):
+        """-> (x_cond [n,T,W], y_cond [n,1,W], prime). Constant for the fixed metas."""
+        n = getattr(y, "n", 1)
+        w = self.prior.w
+        x_cond = w["x_cond"][None].expand(n, -1, -1)
+        y_cond = w["y_cond"][None, None].expand(n, -1, -1)
+        return x_cond, y_cond, None
