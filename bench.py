@@ -315,9 +315,19 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res, prof = timed(step_resident, args.steps, profile=True)
     launches = (model.engine.launches + opt.launches) * args.steps
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+    gemm_flops = sum(f for _, _, f, _ in prof)
     n_gemm = len(prof)
+    by_kind = {}
+    for a, b, f, shp in prof:
+        kind = {(0, 0): "fwd(K,K)", (0, 1): "dgrad(K,MN)", (1, 1): "wgrad(MN,MN)", (1, 0): "(MN,K)"}[shp[3:]]
+        key = f"{kind} M{shp[0]} N{shp[1]} K{shp[2]}"
+        t = by_kind.setdefault(key, [0.0, 0.0, 0])
+        t[0] += f
+        t[1] += a.elapsed_time(b)
+        t[2] += 1
+    by_kind = {k: {"tflops": round(v[0] / (v[1] / 1000.0) / 1e12, 1), "ms_total": round(v[1], 2), "launches": v[2]}
+               for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1])}
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, args.steps)
@@ -356,7 +366,7 @@ def main():
                      "peak_kind": f"{pk_kind} bf16_tflops_sustained", "gemm_launches_timed": n_gemm,
                      "gemm_share_of_step": gemm_ms / ms_res if ms_res else None,
                      "step_tflops_algorithmic": fl["total"] * world * args.steps / (ms_res / 1000.0) / 1e12 / world,
-                     "flops_per_sample": fl["total"] / B},
+                     "flops_per_sample": fl["total"] / B, "gemm_by_shape": by_kind},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -13,7 +13,7 @@ from ._lib import check, lib
 
 BF16 = torch.bfloat16
 
-# bench.py sets this to a list: every gemm() launch then appends (start_event, end_event, flops) recorded on the
+# bench.py sets this to a list: every gemm() launch then appends (start_event, end_event, flops, shape) recorded on the
 # launching stream, which is how the roofline of the dominant kernel is measured live inside the timed region.
 GEMM_PROFILE = None
 
@@ -74,7 +74,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_
     check(rc, f"llark_gemm(M={M},N={N},K={K})")
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K))
+        prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn))))
     return out
 
 
