@@ -44,6 +44,10 @@ int llark_gemm(const void* A, int a_mn_major, long long lda, const void* B, int 
                long long ldc, int c_fp32, const void* bias, int bias_fp32, const void* R, long long ldr, int M, int N,
                int K, int in_fp32, int max_ctas, cudaStream_t stream);
 void llark_gemm_clear_cache(void);
+/* Kernel variant: 1 = CTA-pair kernel (cta_group::2, 256x256 tile per 2-CTA cluster; default), 0 = single-CTA
+ * kernel (128x256 tile). Default comes from the environment variable LLARK_GEMM_2CTA (unset or != "0" -> 1). */
+void llark_gemm_set_mode(int two_cta);
+int llark_gemm_get_mode(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Embedding gather + audio splice (m2t/models/llamav2.py:124 embed_tokens, :141-222 splice loop).

@@ -13,7 +13,7 @@ _ERR = {-1: "LLARK_EINVAL (bad shape/alignment/argument)", -2: "LLARK_ECUDA", -3
 
 # every symbol include/llark_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "llark_last_cuda_error", "llark_gemm", "llark_gemm_clear_cache", "llark_splice_scan", "llark_embed_splice_fwd",
+    "llark_last_cuda_error", "llark_gemm", "llark_gemm_clear_cache", "llark_gemm_set_mode", "llark_gemm_get_mode", "llark_splice_scan", "llark_embed_splice_fwd",
     "llark_embed_splice_bwd", "llark_cast_f32_to_bf16", "llark_cast_bf16_to_f32", "llark_rmsnorm_fwd",
     "llark_rmsnorm_bwd_workspace", "llark_rmsnorm_bwd", "llark_rope", "llark_swiglu_fwd", "llark_swiglu_bwd",
     "llark_attn_fwd", "llark_attn_bwd_workspace", "llark_attn_bwd", "llark_ce_fwd", "llark_ce_bwd",
@@ -48,6 +48,8 @@ def lib():
             "llark_last_cuda_error": ([], I),
             "llark_gemm": ([P, I, LL, P, I, LL, P, LL, I, P, I, P, LL, I, I, I, I, I, P], I),
             "llark_gemm_clear_cache": ([], None),
+            "llark_gemm_set_mode": ([I], None),
+            "llark_gemm_get_mode": ([], I),
             "llark_splice_scan": ([P, I, I, LL, LL, P, P, P, P], I),
             "llark_embed_splice_fwd": ([P, P, P, P, P, P, P, I, I, I, LL, P], I),
             "llark_embed_splice_bwd": ([P, P, P, P, P, P, P, I, I, I, LL, I, P], I),

@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace llark {
 
@@ -76,6 +77,76 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int 
     t.m_blk = first_m + in_group % group_m;
     t.n_blk = in_group / group_m;
     return t;
+}
+
+// One 32-column chunk of one accumulator row: bias / residual, conversion, 16-byte stores (N tail masked).
+__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, long long row, int col0,
+                                     const uint32_t (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int col = col0 + j * 8;
+        if (col >= p.N) break;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+        const bool full8 = (col + 8 <= p.N);
+        if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (full8 || col + e < p.N)
+                    f[e] += p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[col + e]
+                                        : __bfloat162float(
+                                              reinterpret_cast<const __nv_bfloat16*>(p.bias)[col + e]);
+        }
+        if (p.c_fp32) {
+            float* cptr = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
+            if (p.R) {
+                const float* rptr = reinterpret_cast<const float*>(p.R) + row * p.ldr + col;
+                if (full8) {
+                    const float4 r0 = *reinterpret_cast<const float4*>(rptr);
+                    const float4 r1 = *reinterpret_cast<const float4*>(rptr + 4);
+                    f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                    f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                } else {
+                    for (int e = 0; e < 8; ++e)
+                        if (col + e < p.N) f[e] += rptr[e];
+                }
+            }
+            if (full8) {
+                *reinterpret_cast<float4*>(cptr) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(cptr + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+                for (int e = 0; e < 8; ++e)
+                    if (col + e < p.N) cptr[e] = f[e];
+            }
+        } else {
+            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
+            if (p.R) {
+                const __nv_bfloat16* rptr = reinterpret_cast<const __nv_bfloat16*>(p.R) + row * p.ldr + col;
+                if (full8) {
+                    const uint4 r = *reinterpret_cast<const uint4*>(rptr);
+                    const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c2 = unpack_bf16x2(r.z),
+                                 d = unpack_bf16x2(r.w);
+                    f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+                    f[4] += c2.x; f[5] += c2.y; f[6] += d.x; f[7] += d.y;
+                } else {
+                    for (int e = 0; e < 8; ++e)
+                        if (col + e < p.N) f[e] += __bfloat162float(rptr[e]);
+                }
+            }
+            if (full8) {
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(cptr) = o;
+            } else {
+                for (int e = 0; e < 8; ++e)
+                    if (col + e < p.N) cptr[e] = __float2bfloat16_rn(f[e]);
+            }
+        }
+    }
 }
 
 template <int A_MN, int B_MN, int TF32>
@@ -225,71 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * 32, v);
                 tmem_ld_wait();
                 if (!row_ok) continue;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = col0 + j * 8;
-                    if (col >= p.N) break;
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
-                    const bool full8 = (col + 8 <= p.N);
-                    if (p.bias) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (full8 || col + e < p.N)
-                                f[e] += p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[col + e]
-                                                    : __bfloat162float(
-                                                          reinterpret_cast<const __nv_bfloat16*>(p.bias)[col + e]);
-                    }
-                    if (p.c_fp32) {
-                        float* cptr = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
-                        if (p.R) {
-                            const float* rptr = reinterpret_cast<const float*>(p.R) + row * p.ldr + col;
-                            if (full8) {
-                                const float4 r0 = *reinterpret_cast<const float4*>(rptr);
-                                const float4 r1 = *reinterpret_cast<const float4*>(rptr + 4);
-                                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                            } else {
-                                for (int e = 0; e < 8; ++e)
-                                    if (col + e < p.N) f[e] += rptr[e];
-                            }
-                        }
-                        if (full8) {
-                            *reinterpret_cast<float4*>(cptr) = make_float4(f[0], f[1], f[2], f[3]);
-                            *reinterpret_cast<float4*>(cptr + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                        } else {
-                            for (int e = 0; e < 8; ++e)
-                                if (col + e < p.N) cptr[e] = f[e];
-                        }
-                    } else {
-                        __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
-                        if (p.R) {
-                            const __nv_bfloat16* rptr = reinterpret_cast<const __nv_bfloat16*>(p.R) + row * p.ldr + col;
-                            if (full8) {
-                                const uint4 r = *reinterpret_cast<const uint4*>(rptr);
-                                const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c2 = unpack_bf16x2(r.z),
-                                             d = unpack_bf16x2(r.w);
-                                f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
-                                f[4] += c2.x; f[5] += c2.y; f[6] += d.x; f[7] += d.y;
-                            } else {
-                                for (int e = 0; e < 8; ++e)
-                                    if (col + e < p.N) f[e] += __bfloat162float(rptr[e]);
-                            }
-                        }
-                        if (full8) {
-                            uint4 o;
-                            o.x = pack_bf16x2(f[0], f[1]);
-                            o.y = pack_bf16x2(f[2], f[3]);
-                            o.z = pack_bf16x2(f[4], f[5]);
-                            o.w = pack_bf16x2(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(cptr) = o;
-                        } else {
-                            for (int e = 0; e < 8; ++e)
-                                if (col + e < p.N) cptr[e] = __float2bfloat16_rn(f[e]);
-                        }
-                    }
-                }
+                epilogue_store_chunk(p, row, col0, v);
             }
             tc_fence_before();
             __syncwarp();
@@ -302,6 +309,182 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kAccStages * BLOCK_N);
+    }
+}
+
+// =====================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile. CTA r of the
+// pair loads A rows [m0 + 128 r, +128) and B rows (N) [n0 + 128 r, +128) into its own shared memory; the leader
+// (rank 0) issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both CTAs' operands, and each CTA's
+// TMEM receives its 128 accumulator rows x 256 columns. Per SM the shared-memory traffic drops from
+// 96 (TMA writes) + 96 (UMMA reads) B/clk to 64 + 64 B/clk, which is what lets the tensor pipe stay busy.
+constexpr int kStages2 = 6;
+constexpr int B2_STAGE_BYTES = 128 * BLOCK_KB;  // this CTA's half of B: 16 KB
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;  // 32 KB per CTA per stage
+constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 256;
+
+template <int A_MN, int B_MN, int TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+             const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * STAGE2_BYTES);
+    uint64_t* empty_bar = full_bar + kStages2;
+    uint64_t* tmem_full = empty_bar + kStages2;
+    uint64_t* tmem_empty = tmem_full + kAccStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
+    // p.num_m_blocks counts 256-row blocks here
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int elems_per_row = BLOCK_KB / p.elem_bytes;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages2; ++i) {
+            mbar_init(&full_bar[i], 1);   // leader: one arrive.expect_tx covering both CTAs' bytes
+            mbar_init(&empty_bar[i], 1);  // one multicast tcgen05.commit arrive per CTA
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
+        }
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_base_slot, kAccStages * BLOCK_N);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const int m0 = tc.m_blk * 256 + (int)rank * 128;
+            const int n0 = tc.n_blk * BLOCK_N + (int)rank * 128;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * STAGE2_BYTES;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+                const int k0 = kb * elems_per_row;
+                const int mn_per_box = 128 / p.elem_bytes;
+                const int box_bytes = elems_per_row * 128;
+                if (A_MN == 0) {
+                    tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                } else {
+                    for (int j = 0; j < 128 / mn_per_box; ++j)
+                        tma_load_2d_2sm(sa + j * box_bytes, &tma_a, bar, m0 + j * mn_per_box, k0);
+                }
+                if (B_MN == 0) {
+                    tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                } else {
+                    for (int j = 0; j < 128 / mn_per_box; ++j)
+                        tma_load_2d_2sm(sb + j * box_bytes, &tma_b, bar, n0 + j * mn_per_box, k0);
+                }
+                if (++stage == kStages2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        const uint32_t fmt = TF32 ? 2u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const uint32_t mn_box_bytes = elems_per_row * 128;
+        const uint32_t a_lbo = A_MN ? mn_box_bytes : 0, b_lbo = B_MN ? mn_box_bytes : 0;
+        const uint32_t k_rows_per_mma = 32 / p.elem_bytes;
+        const uint32_t a_kstep = A_MN ? (k_rows_per_mma * 128) >> 4 : (32 >> 4);
+        const uint32_t b_kstep = B_MN ? (k_rows_per_mma * 128) >> 4 : (32 >> 4);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+                const uint32_t sb = sa + A_STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
+                const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+                for (int k = 0; k < BLOCK_KB / 32; ++k) {
+                    const uint64_t ad = adesc + (uint64_t)(k * a_kstep);
+                    const uint64_t bd = bdesc + (uint64_t)(k * b_kstep);
+                    if (TF32)
+                        umma_tf32_2sm(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                    else
+                        umma_f16_2sm(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                }
+                umma_commit_2sm(&empty_bar[stage], 3);  // frees the slot in BOTH CTAs
+                if (++stage == kStages2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit_2sm(&tmem_full[as], 3);  // accumulators complete in both CTAs
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int ew = warp - 4;
+        int it = 0;
+        const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)tc.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                const int col0 = tc.n_blk * BLOCK_N + c * 32;
+                if (col0 >= p.N) break;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * 32, v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                epilogue_store_chunk(p, row, col0, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_empty0 + (uint32_t)as * 8u);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    __syncwarp();        // reconverge the single-lane role warps before the warp-aligned cluster barrier
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair still uses its smem / barriers
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, kAccStages * BLOCK_N);
     }
 }
 
@@ -406,11 +589,48 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     return LLARK_OK;
 }
 
+template <int A_MN, int B_MN, int TF32>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas, cudaStream_t stream) {
+    static bool attr_set = false;
+    auto kfn = gemm2_kernel<A_MN, B_MN, TF32>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+        if (e != cudaSuccess) {
+            g_last_cuda_error = (int)e;
+            return LLARK_ECUDA;
+        }
+        attr_set = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    int clusters = g_num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    if (max_ctas > 1 && clusters > max_ctas / 2) clusters = max_ctas / 2;
+    if (clusters < 1) clusters = 1;
+    kfn<<<clusters * 2, kThreads, SMEM2_BYTES, stream>>>(ta, tb, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_ECUDA;
+    }
+    return LLARK_OK;
+}
+
+static int g_gemm_mode = -1;  // -1: read LLARK_GEMM_2CTA from the environment on first use; 0: 1-CTA; 1: CTA pair
+
 }  // namespace llark
 
 using namespace llark;
 
 extern "C" int llark_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" void llark_gemm_set_mode(int two_cta) { g_gemm_mode = two_cta ? 1 : 0; }
+extern "C" int llark_gemm_get_mode(void) {
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("LLARK_GEMM_2CTA");
+        g_gemm_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_gemm_mode;
+}
 
 extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
                           void* C, long long ldc, int c_fp32, const void* bias, int bias_fp32, const void* R,
@@ -434,22 +654,37 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
         rc = get_tensor_map(&ta, A, M, K, lda, epr, epr, eb);  // [K][M], box {128 B of M, epr K-rows}
     if (rc != LLARK_OK) return rc;
     if (!b_mn_major)
-        rc = get_tensor_map(&tb, B, K, N, ldb, epr, BLOCK_N, eb);
+        rc = get_tensor_map(&tb, B, K, N, ldb, epr, llark_gemm_get_mode() ? 128 : BLOCK_N, eb);
     else
         rc = get_tensor_map(&tb, B, N, K, ldb, epr, epr, eb);
     if (rc != LLARK_OK) return rc;
 
+    const int two_cta = llark_gemm_get_mode();
+    const int a_box_rows = BLOCK_M;                 // A rows per CTA (both modes)
+    const int b_box_rows = two_cta ? 128 : BLOCK_N; // B rows (N) per CTA
+    (void)a_box_rows;
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
     p.bias = bias; p.bias_fp32 = bias_fp32;
     p.R = R; p.ldr = ldr;
-    p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    p.num_m_blocks = two_cta ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     p.num_k_blocks = (K + epr - 1) / epr;
     p.elem_bytes = eb;
 
     const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+    if (two_cta) {
+        if (!in_fp32) {
+            switch (sel) {
+                case 0: return launch2<0, 0, 0>(ta, tb, p, max_ctas, stream);
+                case 1: return launch2<0, 1, 0>(ta, tb, p, max_ctas, stream);
+                case 2: return launch2<1, 0, 0>(ta, tb, p, max_ctas, stream);
+                default: return launch2<1, 1, 0>(ta, tb, p, max_ctas, stream);
+            }
+        }
+        return launch2<0, 0, 1>(ta, tb, p, max_ctas, stream);
+    }
     if (!in_fp32) {
         switch (sel) {
             case 0: return launch<0, 0, 0>(ta, tb, p, max_ctas, stream);

@@ -495,46 +495,72 @@ struct AdamArgs {
 //   g  = bf16(g * grad_scale * clip_coef)                (1/(world*accum) scale and clip_grad_norm_)
 //   p  = bf16(p * (1 - lr*wd)); m = bf16(lerp(m, g, 1-b1)); v = bf16(v*b2); v = bf16(v + (1-b2) g g)
 //   den = bf16(bf16(bf16(sqrt(v)) / bc2_sqrt) + eps);  p = bf16(p - (lr/bc1) * m / den)
-__global__ void adamw_kernel(__nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ g,
-                             __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v, long long n,
-                             const float* __restrict__ sumsq, AdamArgs a, int zero_grad) {
+__device__ __forceinline__ void adamw_update8(float (&pf)[8], float (&gf)[8], float (&mf)[8], float (&vf)[8],
+                                              const AdamArgs& a, float clip, float step_size) {
+    const float gs = a.grad_scale;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float gg = gf[e];
+        if (gs != 1.f) gg = bf16_round(gg * gs);
+        if (clip != 1.f) gg = bf16_round(gg * clip);
+        float pp = pf[e];
+        if (a.weight_decay != 0.f) pp = bf16_round(pp * (1.f - a.lr * a.weight_decay));
+        const float w = 1.f - a.beta1;
+        const float mm = bf16_round(w < 0.5f ? mf[e] + w * (gg - mf[e]) : gg - (gg - mf[e]) * (1.f - w));
+        float vv = bf16_round(vf[e] * a.beta2);
+        vv = bf16_round(vv + (1.f - a.beta2) * gg * gg);
+        float den = bf16_round(sqrtf(vv));
+        den = bf16_round(den / a.bc2_sqrt);
+        den = bf16_round(den + a.eps);
+        pp = bf16_round(pp - step_size * (mm / den));
+        pf[e] = pp; mf[e] = mm; vf[e] = vv;
+        gf[e] = 0.f;
+    }
+}
+
+// Two 16-byte vectors of each of the four streams are in flight per thread (8 independent 16 B loads) before any
+// arithmetic: the kernel is a pure HBM stream (read p,g,m,v; write p,m,v and the zeroed g).
+__global__ void __launch_bounds__(256)
+adamw_kernel(__nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ m,
+             __nv_bfloat16* __restrict__ v, long long n, const float* __restrict__ sumsq, AdamArgs a, int zero_grad) {
     float clip = 1.f;
     if (sumsq && a.max_norm > 0.f) {
         const float total = sqrtf(sumsq[0]) * a.grad_scale;
         clip = fminf(1.f, a.max_norm / (total + 1e-6f));
     }
-    const float gs = a.grad_scale;
     const float step_size = a.lr / a.bc1;
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    const long long stride = (long long)gridDim.x * blockDim.x * 8;
-    for (; i + 8 <= n; i += stride) {
-        float pf[8], gf[8], mf[8], vf[8];
-        load8(p + i, pf);
-        load8(g + i, gf);
-        load8(m + i, mf);
-        load8(v + i, vf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float gg = gf[e];
-            if (gs != 1.f) gg = bf16_round(gg * gs);
-            if (clip != 1.f) gg = bf16_round(gg * clip);
-            float pp = pf[e];
-            if (a.weight_decay != 0.f) pp = bf16_round(pp * (1.f - a.lr * a.weight_decay));
-            const float w = 1.f - a.beta1;
-            const float mm = bf16_round(w < 0.5f ? mf[e] + w * (gg - mf[e]) : gg - (gg - mf[e]) * (1.f - w));
-            float vv = bf16_round(vf[e] * a.beta2);
-            vv = bf16_round(vv + (1.f - a.beta2) * gg * gg);
-            float den = bf16_round(sqrtf(vv));
-            den = bf16_round(den / a.bc2_sqrt);
-            den = bf16_round(den + a.eps);
-            pp = bf16_round(pp - step_size * (mm / den));
-            pf[e] = pp; mf[e] = mm; vf[e] = vv;
-            gf[e] = 0.f;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long nvec = n / 8;
+    // vectors tid, tid + nthreads (coalesced within each of the two halves of the iteration)
+    for (long long base = tid; base < nvec; base += 2 * nthreads) {
+        const long long i0 = base * 8;
+        const long long v1 = base + nthreads;
+        const bool has1 = v1 < nvec;
+        const long long i1 = v1 * 8;
+        float p0[8], g0[8], m0[8], w0[8], p1[8], g1[8], m1[8], w1[8];
+        load8(p + i0, p0);
+        load8(g + i0, g0);
+        load8(m + i0, m0);
+        load8(v + i0, w0);
+        if (has1) {
+            load8(p + i1, p1);
+            load8(g + i1, g1);
+            load8(m + i1, m1);
+            load8(v + i1, w1);
         }
-        store8(p + i, pf);
-        store8(m + i, mf);
-        store8(v + i, vf);
-        if (zero_grad) store8(g + i, gf);
+        adamw_update8(p0, g0, m0, w0, a, clip, step_size);
+        store8(p + i0, p0);
+        store8(m + i0, m0);
+        store8(v + i0, w0);
+        if (zero_grad) store8(g + i0, g0);
+        if (has1) {
+            adamw_update8(p1, g1, m1, w1, a, clip, step_size);
+            store8(p + i1, p1);
+            store8(m + i1, m1);
+            store8(v + i1, w1);
+            if (zero_grad) store8(g + i1, g1);
+        }
     }
 }
 
@@ -712,7 +738,7 @@ extern "C" int llark_adamw_step(void* p, void* g, void* m, void* v, long long n,
     a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.grad_scale = grad_scale; a.max_norm = max_norm;
-    adamw_kernel<<<grid_for(n / 8, 256, 148 * 8), 256, 0, st>>>((__nv_bfloat16*)p, (__nv_bfloat16*)g, (__nv_bfloat16*)m,
+    adamw_kernel<<<grid_for(n / 16, 256, 148 * 8), 256, 0, st>>>((__nv_bfloat16*)p, (__nv_bfloat16*)g, (__nv_bfloat16*)m,
                                                                 (__nv_bfloat16*)v, n, sumsq, a, zero_grad);
     return check_launch();
 }

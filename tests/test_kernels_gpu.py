@@ -25,6 +25,17 @@ def _rel(a, b):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
+@pytest.fixture(params=[1, 0], ids=["cta_pair", "single_cta"])
+def gemm_mode(request):
+    """Run every GEMM test on both kernel variants (cta_group::2 pair kernel and the single-CTA kernel)."""
+    from llark_b200._lib import lib
+
+    old = lib().llark_gemm_get_mode()
+    lib().llark_gemm_set_mode(request.param)
+    yield request.param
+    lib().llark_gemm_set_mode(old)
+
+
 GEMM_SHAPES = [
     (128, 256, 64), (128, 256, 256), (256, 512, 4096), (240, 4096, 4800), (512, 1000, 256), (384, 768, 1000),
     (100, 72, 136), (1024, 4096, 4096),
@@ -33,7 +44,7 @@ GEMM_SHAPES = [
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_bf16(M, N, K, a_mn, b_mn):
+def test_gemm_bf16(M, N, K, a_mn, b_mn, gemm_mode):
     ops = _ops()
     torch.manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(M, K, device="cuda") * 0.5
@@ -52,7 +63,7 @@ def test_gemm_bf16(M, N, K, a_mn, b_mn):
     assert _rel(out, ref) < 5e-3, (err, scale)
 
 
-def test_gemm_bias_residual_and_fp32_out():
+def test_gemm_bias_residual_and_fp32_out(gemm_mode):
     ops = _ops()
     torch.manual_seed(0)
     M, N, K = 300, 520, 192
@@ -82,7 +93,7 @@ def test_gemm_tf32_mn_major_rejected():
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False)])
-def test_gemm_tf32(a_mn, b_mn):
+def test_gemm_tf32(a_mn, b_mn, gemm_mode):
     ops = _ops()
     torch.manual_seed(1)
     M, N, K = 256, 1200, 4800
@@ -97,7 +108,7 @@ def test_gemm_tf32(a_mn, b_mn):
     assert _rel(out, ref) < 2e-3
 
 
-def test_gemm_persistent_many_tiles_and_ld():
+def test_gemm_persistent_many_tiles_and_ld(gemm_mode):
     """More tiles than SMs (several waves per CTA), padded leading dimensions, partial N tile."""
     ops = _ops()
     torch.manual_seed(2)

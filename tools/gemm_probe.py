@@ -6,6 +6,8 @@ import torch
 from llark_b200 import ops
 
 a_mn, b_mn, fp32 = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+from llark_b200._lib import lib
+print("gemm mode (1 = CTA pair):", lib().llark_gemm_get_mode(), flush=True)
 dt = torch.float32 if fp32 else torch.bfloat16
 shapes = [(128, 256, 16), (128, 256, 32), (128, 256, 64), (128, 256, 128), (128, 256, 256), (128, 256, 512),
           (256, 256, 64), (128, 512, 64), (256, 512, 320), (4096, 4096, 4096), (64, 64, 64), (240, 4096, 4800)]
@@ -35,24 +37,24 @@ for (M, N, K) in shapes:
         break
 # quick timing of the big one
 if not fp32:
-    M = N = K = 8192
-    a = torch.randn(M, K, device="cuda").to(dt); b = torch.randn(N, K, device="cuda").to(dt)
-    ai = a.t().contiguous() if a_mn else a
-    bi = b.t().contiguous() if b_mn else b
-    out = torch.empty(M, N, device="cuda", dtype=dt)
-    for _ in range(3): ops.gemm(ai, bi, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): ops.gemm(ai, bi, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"timing a_mn={a_mn} b_mn={b_mn} 8192^3: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
-    ref = torch.matmul(a, b.t())
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    for _ in range(3): torch.matmul(a, b.t(), out=ref)
-    t0.record()
-    for _ in range(10): torch.matmul(a, b.t(), out=ref)
-    t1.record(); torch.cuda.synchronize()
-    ms2 = t0.elapsed_time(t1) / 10
-    print(f"timing cublas 8192^3: {ms2:.3f} ms  {2*M*N*K/ms2/1e9:.1f} TFLOP/s", flush=True)
+  for (M, N, K) in ((8192, 8192, 8192), (4096, 12288, 4096), (4096, 4096, 11008), (4096, 22016, 4096)):
+      a = torch.randn(M, K, device="cuda").to(dt); b = torch.randn(N, K, device="cuda").to(dt)
+      ai = a.t().contiguous() if a_mn else a
+      bi = b.t().contiguous() if b_mn else b
+      out = torch.empty(M, N, device="cuda", dtype=dt)
+      for _ in range(3): ops.gemm(ai, bi, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out)
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(10): ops.gemm(ai, bi, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out)
+      e1.record(); torch.cuda.synchronize()
+      ms = e0.elapsed_time(e1) / 10
+      print(f"timing a_mn={a_mn} b_mn={b_mn} {M}x{N}x{K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+      ref = torch.matmul(a, b.t())
+      t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+      for _ in range(3): torch.matmul(a, b.t(), out=ref)
+      t0.record()
+      for _ in range(10): torch.matmul(a, b.t(), out=ref)
+      t1.record(); torch.cuda.synchronize()
+      ms2 = t0.elapsed_time(t1) / 10
+      print(f"timing cublas {M}x{N}x{K}: {ms2:.3f} ms  {2*M*N*K/ms2/1e9:.1f} TFLOP/s", flush=True)
