@@ -47,6 +47,9 @@ struct GemmParams {
     long long ldr;
     int num_m_blocks, num_n_blocks, num_k_blocks;
     int elem_bytes;  // 2 (bf16) or 4 (tf32)
+    int a_tma4, b_tma4;  // MN-major operand loaded by ONE 4-D TMA box per stage (atom order: 64 MN, 8 K, chunks, K-groups)
+    int debug;       // LLARK_GEMM_DEBUG bits (perf experiments only): 1 = split K-major boxes in 64-row halves,
+                     // 2 = producer issues no TMA (MMA runs on stale smem: isolates the UMMA rate)
 };
 
 // SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -384,18 +387,42 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 uint8_t* sa = smem + stage * STAGE2_BYTES;
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+                if (p.debug & 2) {
+                    if (leader) mbar_arrive(&full_bar[stage]);
+                    if (++stage == kStages2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    continue;
+                }
                 if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
                 const int k0 = kb * elems_per_row;
                 const int mn_per_box = 128 / p.elem_bytes;
                 const int box_bytes = elems_per_row * 128;
                 if (A_MN == 0) {
-                    tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                    if (p.debug & 1) {
+                        tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                        tma_load_2d_2sm(sa + 64 * 128, &tma_a, bar, k0, m0 + 64);
+                    } else
+                        tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                } else if (p.a_tma4 == 2) {
+                    tma_load_3d_2sm(sa, &tma_a, bar, 0, k0, m0 / mn_per_box);
+                } else if (p.a_tma4) {
+                    tma_load_4d_2sm(sa, &tma_a, bar, 0, 0, m0 / mn_per_box, k0 / 8);
                 } else {
                     for (int j = 0; j < 128 / mn_per_box; ++j)
                         tma_load_2d_2sm(sa + j * box_bytes, &tma_a, bar, m0 + j * mn_per_box, k0);
                 }
                 if (B_MN == 0) {
-                    tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                    if (p.debug & 1) {
+                        tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                        tma_load_2d_2sm(sb + 64 * 128, &tma_b, bar, k0, n0 + 64);
+                    } else
+                        tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                } else if (p.b_tma4 == 2) {
+                    tma_load_3d_2sm(sb, &tma_b, bar, 0, k0, n0 / mn_per_box);
+                } else if (p.b_tma4) {
+                    tma_load_4d_2sm(sb, &tma_b, bar, 0, 0, n0 / mn_per_box, k0 / 8);
                 } else {
                     for (int j = 0; j < 128 / mn_per_box; ++j)
                         tma_load_2d_2sm(sb + j * box_bytes, &tma_b, bar, n0 + j * mn_per_box, k0);
@@ -409,13 +436,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     } else if (warp == 1 && lane == 0 && leader) {
         // ===================== MMA issuer (leader CTA only) =====================
         const uint32_t fmt = TF32 ? 2u : 1u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+        // debug bit 4 (timing experiment only, wrong results): read the operands as MN-major although the TMA
+        // loaded them K-major -- separates "MN-major UMMA smem reads" from "MN-major global access pattern".
+        const uint32_t amn = (p.debug & 4) ? 1u : ((p.debug & 8) ? 0u : (uint32_t)A_MN);
+        const uint32_t bmn = (p.debug & 4) ? 1u : ((p.debug & 8) ? 0u : (uint32_t)B_MN);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (amn << 15) | (bmn << 16) |
                                ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         const uint32_t mn_box_bytes = elems_per_row * 128;
-        const uint32_t a_lbo = A_MN ? mn_box_bytes : 0, b_lbo = B_MN ? mn_box_bytes : 0;
+        // MN-major smem layouts. 2-D path: [chunk][K rows][128 B]   -> LBO = box bytes, SBO = 1024, K-step = rows*128
+        //                        4-D path: [K group][chunk][8][128 B] -> LBO = 1024, SBO = chunks*1024 (2 chunks = 128 MN)
         const uint32_t k_rows_per_mma = 32 / p.elem_bytes;
-        const uint32_t a_kstep = A_MN ? (k_rows_per_mma * 128) >> 4 : (32 >> 4);
-        const uint32_t b_kstep = B_MN ? (k_rows_per_mma * 128) >> 4 : (32 >> 4);
+        const bool a4 = p.a_tma4 == 1, b4 = p.b_tma4 == 1;  // (== 2: 3-D box, same smem layout as the 2-D path)
+        const uint32_t a_lbo = amn ? (a4 ? 1024u : mn_box_bytes) : 0u;
+        const uint32_t b_lbo = bmn ? (b4 ? 1024u : mn_box_bytes) : 0u;
+        const uint32_t a_sbo = (amn && a4) ? 2048u : 1024u;
+        const uint32_t b_sbo = (bmn && b4) ? 2048u : 1024u;
+        const uint32_t a_kstep = amn ? ((a4 ? (k_rows_per_mma / 8) * 2048u : k_rows_per_mma * 128u) >> 4) : (32 >> 4);
+        const uint32_t b_kstep = bmn ? ((b4 ? (k_rows_per_mma / 8) * 2048u : k_rows_per_mma * 128u) >> 4) : (32 >> 4);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -430,8 +467,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
                 const uint32_t sb = sa + A_STAGE_BYTES;
-                const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024);
-                const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024);
+                const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo);
+                const uint64_t bdesc = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
                 for (int k = 0; k < BLOCK_KB / 32; ++k) {
                     const uint64_t ad = adesc + (uint64_t)(k * a_kstep);
@@ -565,6 +602,75 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, long long inner, lo
     return LLARK_OK;
 }
 
+// 4-D tensor map over a row-major [K][ld] array ([K][MN] valid, MN contiguous) that delivers a whole MN-major
+// operand stage with ONE box: dims (128 B of MN, 8 K rows, MN chunks, K groups of 8), box (.., 8, chunks, kgroups).
+static int get_tensor_map_mn4(CUtensorMap* out, const void* ptr, long long mn, long long k, long long ld, int chunks,
+                              int kgroups, int elem_bytes) {
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.inner = mn; key.outer = k; key.ld = ld;
+    key.box_inner = -chunks; key.box_outer = kgroups; key.elem = elem_bytes;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto itf = g_map_cache.find(key);
+        if (itf != g_map_cache.end()) {
+            *out = itf->second;
+            return LLARK_OK;
+        }
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) return LLARK_EINVAL;
+    const int epc = 128 / elem_bytes;
+    cuuint64_t gdim[4] = {(cuuint64_t)epc, 8, (cuuint64_t)(mn / epc), (cuuint64_t)(k / 8)};
+    cuuint64_t gstride[3] = {(cuuint64_t)(ld * elem_bytes), 128, (cuuint64_t)(8 * ld * elem_bytes)};
+    cuuint32_t box[4] = {(cuuint32_t)epc, 8, (cuuint32_t)chunks, (cuuint32_t)kgroups};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                          const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return LLARK_EDRIVER;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_map_cache[key] = *out;
+    return LLARK_OK;
+}
+
+// 3-D variant: dims (128 B of MN, K rows, MN chunks), box (.., krows, chunks): smem layout [chunk][K rows][128 B].
+static int get_tensor_map_mn3(CUtensorMap* out, const void* ptr, long long mn, long long k, long long ld, int chunks,
+                              int krows, int elem_bytes) {
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.inner = mn; key.outer = k; key.ld = ld;
+    key.box_inner = -100 - chunks; key.box_outer = krows; key.elem = elem_bytes;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto itf = g_map_cache.find(key);
+        if (itf != g_map_cache.end()) {
+            *out = itf->second;
+            return LLARK_OK;
+        }
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) return LLARK_EINVAL;
+    const int epc = 128 / elem_bytes;
+    cuuint64_t gdim[3] = {(cuuint64_t)epc, (cuuint64_t)k, (cuuint64_t)(mn / epc)};
+    cuuint64_t gstride[2] = {(cuuint64_t)(ld * elem_bytes), 128};
+    cuuint32_t box[3] = {(cuuint32_t)epc, (cuuint32_t)krows, (cuuint32_t)chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return LLARK_EDRIVER;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_map_cache[key] = *out;
+    return LLARK_OK;
+}
+
 template <int A_MN, int B_MN, int TF32>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas, cudaStream_t stream) {
     static bool attr_set = false;
@@ -647,14 +753,36 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
     if ((ldc % vec) != 0 || (reinterpret_cast<uintptr_t>(C) & 15) != 0) return LLARK_EINVAL;
     if (R && ((ldr % vec) != 0 || (reinterpret_cast<uintptr_t>(R) & 15) != 0)) return LLARK_EINVAL;
 
+    static int dbg_split = -1;
+    if (dbg_split < 0) {
+        const char* e = getenv("LLARK_GEMM_DEBUG");
+        dbg_split = (e && (atoi(e) & 1)) ? 1 : 0;
+    }
+    // MN-major operands of the CTA-pair kernel use the one-box 4-D load when the extents tile exactly
+    static int use4 = -1;
+    if (use4 < 0) {
+        const char* e = getenv("LLARK_GEMM_TMA4");
+        use4 = e ? atoi(e) : 2;  // 0: 2-D boxes, 1: one 4-D box, 2: one 3-D box (default)
+    }
+    const int epc_ = 128 / eb;
+    const bool a4 = use4 && llark_gemm_get_mode() && a_mn_major && !in_fp32 && (M % epc_ == 0) && (K % 8 == 0);
+    const bool b4 = use4 && llark_gemm_get_mode() && b_mn_major && !in_fp32 && (N % epc_ == 0) && (K % 8 == 0);
     CUtensorMap ta, tb;
-    if (!a_mn_major)
-        rc = get_tensor_map(&ta, A, K, M, lda, epr, BLOCK_M, eb);  // [M][K], box {K-row 128 B, 128 rows}
+    if (a4 && use4 == 2)
+        rc = get_tensor_map_mn3(&ta, A, M, K, lda, 2, epr, eb);
+    else if (a4)
+        rc = get_tensor_map_mn4(&ta, A, M, K, lda, 2, epr / 8, eb);
+    else if (!a_mn_major)
+        rc = get_tensor_map(&ta, A, K, M, lda, epr, dbg_split ? 64 : BLOCK_M, eb);  // [M][K], box {128 B, 128 rows}
     else
         rc = get_tensor_map(&ta, A, M, K, lda, epr, epr, eb);  // [K][M], box {128 B of M, epr K-rows}
     if (rc != LLARK_OK) return rc;
-    if (!b_mn_major)
-        rc = get_tensor_map(&tb, B, K, N, ldb, epr, llark_gemm_get_mode() ? 128 : BLOCK_N, eb);
+    if (b4 && use4 == 2)
+        rc = get_tensor_map_mn3(&tb, B, N, K, ldb, 2, epr, eb);
+    else if (b4)
+        rc = get_tensor_map_mn4(&tb, B, N, K, ldb, 2, epr / 8, eb);
+    else if (!b_mn_major)
+        rc = get_tensor_map(&tb, B, K, N, ldb, epr, dbg_split ? 64 : (llark_gemm_get_mode() ? 128 : BLOCK_N), eb);
     else
         rc = get_tensor_map(&tb, B, N, K, ldb, epr, epr, eb);
     if (rc != LLARK_OK) return rc;
@@ -672,6 +800,16 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
     p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     p.num_k_blocks = (K + epr - 1) / epr;
     p.elem_bytes = eb;
+    p.a_tma4 = a4 ? use4 : 0;
+    p.b_tma4 = b4 ? use4 : 0;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("LLARK_GEMM_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.debug = dbg;
+    }
 
     const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
     if (two_cta) {

@@ -175,7 +175,7 @@ def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0):
     hps = SimpleNamespace(sr=JUKEBOX_SAMPLE_RATE, n_samples=8, name="samples", levels=3,
                           hop_fraction=[0.5, 0.5, 0.125], sample_length=cfg.sample_length)
     vq_state, prior_state = state if state is not None else (random_vqvae_state(cfg, seed),
-                                                             random_prior_state(cfg, seed + 1))
+                                                             random_prior_state(cfg, seed + 1, device="cuda"))
     vqvae = JukeboxVQVAE(cfg, vq_state)
     top_prior = JukeboxTopPrior(cfg, prior_state, precision=precision)
     return hps, vqvae, top_prior

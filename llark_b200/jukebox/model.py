@@ -113,27 +113,36 @@ class JukeboxVQVAE:
         return [None, None, z]
 
 
-def random_prior_state(cfg, seed=1):
-    g = torch.Generator().manual_seed(seed)
+def random_prior_state(cfg, seed=1, device="cpu"):
+    """Seeded synthetic prior weights of the upstream shapes; pass device="cuda" to create the 2.5 G parameters of
+    the real 36-layer prior directly in HBM."""
+    g = torch.Generator(device=device).manual_seed(seed)
     W, A, Mw = cfg.prior_width, cfg.attn_width, cfg.mlp_width
-    st = {"x_emb": torch.randn(cfg.l_bins, W, generator=g) * 0.02,
-          "pos_emb": torch.randn(cfg.n_ctx, W, generator=g) * 0.01,
-          "x_cond": torch.randn(cfg.n_ctx, W, generator=g) * 0.01,
-          "y_cond": torch.randn(W, generator=g) * 0.02}
+
+    class _R:
+        @staticmethod
+        def randn(*shape, generator=None):
+            return torch.randn(*shape, generator=generator, device=device)
+
+    randn = _R.randn
+    st = {"x_emb": randn(cfg.l_bins, W, generator=g) * 0.02,
+          "pos_emb": randn(cfg.n_ctx, W, generator=g) * 0.01,
+          "x_cond": randn(cfg.n_ctx, W, generator=g) * 0.01,
+          "y_cond": randn(W, generator=g) * 0.02}
     for d in range(cfg.prior_depth):
         q = f"blk.{d}."
-        st[q + "ln0.g"] = 1 + 0.1 * torch.randn(W, generator=g)
-        st[q + "ln0.b"] = 0.02 * torch.randn(W, generator=g)
-        st[q + "c_attn.w"] = torch.randn(W, 3 * A, generator=g) * (0.7 / math.sqrt(W))
-        st[q + "c_attn.b"] = 0.02 * torch.randn(3 * A, generator=g)
-        st[q + "c_proj.w"] = torch.randn(A, W, generator=g) * (0.3 / math.sqrt(A))
-        st[q + "c_proj.b"] = 0.02 * torch.randn(W, generator=g)
-        st[q + "ln1.g"] = 1 + 0.1 * torch.randn(W, generator=g)
-        st[q + "ln1.b"] = 0.02 * torch.randn(W, generator=g)
-        st[q + "fc.w"] = torch.randn(W, Mw, generator=g) * (0.7 / math.sqrt(W))
-        st[q + "fc.b"] = 0.02 * torch.randn(Mw, generator=g)
-        st[q + "fc_proj.w"] = torch.randn(Mw, W, generator=g) * (0.3 / math.sqrt(Mw))
-        st[q + "fc_proj.b"] = 0.02 * torch.randn(W, generator=g)
+        st[q + "ln0.g"] = 1 + 0.1 * randn(W, generator=g)
+        st[q + "ln0.b"] = 0.02 * randn(W, generator=g)
+        st[q + "c_attn.w"] = randn(W, 3 * A, generator=g) * (0.7 / math.sqrt(W))
+        st[q + "c_attn.b"] = 0.02 * randn(3 * A, generator=g)
+        st[q + "c_proj.w"] = randn(A, W, generator=g) * (0.3 / math.sqrt(A))
+        st[q + "c_proj.b"] = 0.02 * randn(W, generator=g)
+        st[q + "ln1.g"] = 1 + 0.1 * randn(W, generator=g)
+        st[q + "ln1.b"] = 0.02 * randn(W, generator=g)
+        st[q + "fc.w"] = randn(W, Mw, generator=g) * (0.7 / math.sqrt(W))
+        st[q + "fc.b"] = 0.02 * randn(Mw, generator=g)
+        st[q + "fc_proj.w"] = randn(Mw, W, generator=g) * (0.3 / math.sqrt(Mw))
+        st[q + "fc_proj.b"] = 0.02 * randn(W, generator=g)
     return st
 
 
