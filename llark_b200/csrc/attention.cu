@@ -47,6 +47,26 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
     }
 }
 
+// Asynchronous variant (cp.async, 16 B per request, zero-fill for rows >= valid): lets the next K/V tile stream
+// into the other shared-memory buffer while the tensor cores work on the current one.
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int ROWS>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, long long gstride, int valid) {
+    for (int i = threadIdx.x; i < ROWS * 16; i += blockDim.x) {
+        const int r = i >> 4, c = (i & 15) * 8;
+        const bool ok = r < valid;
+        cp_async_16(s + r * LDS + c, g + (long long)(ok ? r : 0) * gstride + c, ok);
+    }
+}
+
 // A-operand fragment address (16 rows x 16 k) for ldmatrix.x4: matrices (r0-7,k0-7) (r8-15,k0-7) (r0-7,k8-15) (r8-15,k8-15)
 __device__ __forceinline__ const __nv_bfloat16* a_addr(const __nv_bfloat16* s, int row0, int k0, int lane) {
     return s + (row0 + (lane & 15)) * LDS + k0 + (lane >> 4) * 8;
@@ -67,9 +87,9 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __re
                 __nv_bfloat16* __restrict__ O, float* __restrict__ lse_out, int S, int NH, float scale_log2) {
     extern __shared__ __align__(16) uint8_t smem_attn[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-    __nv_bfloat16* sK = sQ + 64 * LDS;
-    __nv_bfloat16* sV = sK + 64 * LDS;
-    float* sMask = reinterpret_cast<float*>(sV + 64 * LDS);
+    __nv_bfloat16* sKb = sQ + 64 * LDS;        // two K buffers
+    __nv_bfloat16* sVb = sKb + 2 * 64 * LDS;   // two V buffers
+    float* sMaskb = reinterpret_cast<float*>(sVb + 2 * 64 * LDS);  // two mask rows
 
     const int qt = gridDim.x - 1 - blockIdx.x;  // longest rows first
     const int h = blockIdx.y, b = blockIdx.z;
@@ -93,17 +113,29 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __re
         for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-    for (int kt = 0; kt <= qt; ++kt) {
-        const int k0 = kt * 64;
-        __syncthreads();
-        load_tile<64>(sK, kbase + (long long)k0 * rs, rs, min(64, S - k0));
-        load_tile<64>(sV, vbase + (long long)k0 * rs, rs, min(64, S - k0));
+    auto prefetch = [&](int kt) {
+        const int k0 = kt * 64, buf = kt & 1;
+        load_tile_async<64>(sKb + buf * 64 * LDS, kbase + (long long)k0 * rs, rs, min(64, S - k0));
+        load_tile_async<64>(sVb + buf * 64 * LDS, vbase + (long long)k0 * rs, rs, min(64, S - k0));
         if (threadIdx.x < 64) {
             const int kk = k0 + threadIdx.x;
             const bool ok = kk < S && (!mask || mask[(long long)b * S + kk] != 0);
-            sMask[threadIdx.x] = ok ? 0.f : -INFINITY;
+            sMaskb[buf * 64 + threadIdx.x] = ok ? 0.f : -INFINITY;
+        }
+        cp_async_commit();
+    };
+    prefetch(0);
+    for (int kt = 0; kt <= qt; ++kt) {
+        if (kt < qt) {
+            prefetch(kt + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const __nv_bfloat16* sK = sKb + (kt & 1) * 64 * LDS;
+        const __nv_bfloat16* sV = sVb + (kt & 1) * 64 * LDS;
+        const float* sMask = sMaskb + (kt & 1) * 64;
 
         float s[8][4];
 #pragma unroll
@@ -173,6 +205,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __re
                 mma16816(o[2 * j + 1], pa, vb[2], vb[3]);
             }
         }
+        __syncthreads();  // all warps are done with this buffer before the next prefetch overwrites it
     }
 
 #pragma unroll
@@ -229,10 +262,10 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char*
     extern __shared__ __align__(16) uint8_t smem_attn[];
     __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);
     __nv_bfloat16* sV = sK + 64 * LDS;
-    __nv_bfloat16* sQ = sV + 64 * LDS;
-    __nv_bfloat16* sdO = sQ + 32 * LDS;
-    float* sLse = reinterpret_cast<float*>(sdO + 32 * LDS);  // 32, log2 domain
-    float* sD = sLse + 32;
+    __nv_bfloat16* sQb = sV + 64 * LDS;            // two Q buffers (32 rows each)
+    __nv_bfloat16* sdOb = sQb + 2 * 32 * LDS;      // two dO buffers
+    float* sLseb = reinterpret_cast<float*>(sdOb + 2 * 32 * LDS);  // 2 x 32, log2 domain
+    float* sDb = sLseb + 64;
 
     const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,17 +294,32 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char*
 #pragma unroll
         for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
 
-    for (int q0 = k0; q0 < S; q0 += 32) {
-        __syncthreads();
-        load_tile<32>(sQ, qbase + (long long)q0 * rs, rs, min(32, S - q0));
-        load_tile<32>(sdO, dobase + (long long)q0 * os, os, min(32, S - q0));
+    auto prefetch = [&](int q0, int buf) {
+        load_tile_async<32>(sQb + buf * 32 * LDS, qbase + (long long)q0 * rs, rs, min(32, S - q0));
+        load_tile_async<32>(sdOb + buf * 32 * LDS, dobase + (long long)q0 * os, os, min(32, S - q0));
         if (threadIdx.x < 32) {
             const int qq = q0 + threadIdx.x;
             const bool ok = qq < S;
-            sLse[threadIdx.x] = ok ? lse[((long long)b * NH + h) * S + qq] * LOG2E : INFINITY;
-            sD[threadIdx.x] = ok ? Dsum[((long long)b * NH + h) * S + qq] : 0.f;
+            sLseb[buf * 32 + threadIdx.x] = ok ? lse[((long long)b * NH + h) * S + qq] * LOG2E : INFINITY;
+            sDb[buf * 32 + threadIdx.x] = ok ? Dsum[((long long)b * NH + h) * S + qq] : 0.f;
+        }
+        cp_async_commit();
+    };
+    __syncthreads();  // K/V tiles (synchronous loads above) visible
+    prefetch(k0, 0);
+    int it = 0;
+    for (int q0 = k0; q0 < S; q0 += 32, ++it) {
+        if (q0 + 32 < S) {
+            prefetch(q0 + 32, (it + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const __nv_bfloat16* sQ = sQb + (it & 1) * 32 * LDS;
+        const __nv_bfloat16* sdO = sdOb + (it & 1) * 32 * LDS;
+        const float* sLse = sLseb + (it & 1) * 32;
+        const float* sD = sDb + (it & 1) * 32;
 
         // S^T = K Q^T  (16 keys x 32 queries), dP^T = V dO^T
         float st[4][4], dpt[4][4];
@@ -331,6 +379,7 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char*
                 mma16816(dk[2 * j + 1], sa, qb[2], qb[3]);
             }
         }
+        __syncthreads();
     }
 
 #pragma unroll
@@ -357,9 +406,9 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* _
     extern __shared__ __align__(16) uint8_t smem_attn[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
     __nv_bfloat16* sdO = sQ + 64 * LDS;
-    __nv_bfloat16* sK = sdO + 64 * LDS;
-    __nv_bfloat16* sV = sK + 64 * LDS;
-    float* sMask = reinterpret_cast<float*>(sV + 64 * LDS);  // 64: 1 = key allowed
+    __nv_bfloat16* sKb = sdO + 64 * LDS;
+    __nv_bfloat16* sVb = sKb + 2 * 64 * LDS;
+    float* sMaskb = reinterpret_cast<float*>(sVb + 2 * 64 * LDS);  // 2 x 64: 1 = key allowed
 
     const int qt = gridDim.x - 1 - blockIdx.x;
     const int h = blockIdx.y, b = blockIdx.z;
@@ -390,16 +439,28 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* _
 #pragma unroll
         for (int e = 0; e < 4; ++e) dq[i][e] = 0.f;
 
-    for (int kt = 0; kt <= qt; ++kt) {
-        const int k0 = kt * 64;
-        __syncthreads();
-        load_tile<64>(sK, kbase + (long long)k0 * rs, rs, min(64, S - k0));
-        load_tile<64>(sV, vbase + (long long)k0 * rs, rs, min(64, S - k0));
+    auto prefetch = [&](int kt) {
+        const int k0 = kt * 64, buf = kt & 1;
+        load_tile_async<64>(sKb + buf * 64 * LDS, kbase + (long long)k0 * rs, rs, min(64, S - k0));
+        load_tile_async<64>(sVb + buf * 64 * LDS, vbase + (long long)k0 * rs, rs, min(64, S - k0));
         if (threadIdx.x < 64) {
             const int kk = k0 + threadIdx.x;
-            sMask[threadIdx.x] = (kk < S && (!mask || mask[(long long)b * S + kk] != 0)) ? 1.f : 0.f;
+            sMaskb[buf * 64 + threadIdx.x] = (kk < S && (!mask || mask[(long long)b * S + kk] != 0)) ? 1.f : 0.f;
+        }
+        cp_async_commit();
+    };
+    prefetch(0);
+    for (int kt = 0; kt <= qt; ++kt) {
+        if (kt < qt) {
+            prefetch(kt + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const __nv_bfloat16* sK = sKb + (kt & 1) * 64 * LDS;
+        const __nv_bfloat16* sV = sVb + (kt & 1) * 64 * LDS;
+        const float* sMask = sMaskb + (kt & 1) * 64;
 
         float s[8][4], dp[8][4];
 #pragma unroll
@@ -448,6 +509,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* _
                 mma16816(dq[2 * j + 1], sa, kb[2], kb[3]);
             }
         }
+        __syncthreads();
     }
 
 #pragma unroll
@@ -463,9 +525,9 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* _
     }
 }
 
-constexpr int FWD_SMEM = 3 * 64 * LDS * 2 + 64 * 4;
-constexpr int DKDV_SMEM = (2 * 64 + 2 * 32) * LDS * 2 + 64 * 4;
-constexpr int DQ_SMEM = 4 * 64 * LDS * 2 + 64 * 4;
+constexpr int FWD_SMEM = 5 * 64 * LDS * 2 + 2 * 64 * 4;
+constexpr int DKDV_SMEM = (2 * 64 + 4 * 32) * LDS * 2 + 128 * 4;
+constexpr int DQ_SMEM = 6 * 64 * LDS * 2 + 2 * 64 * 4;
 
 static int set_smem(const void* fn, int bytes) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

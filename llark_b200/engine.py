@@ -53,6 +53,9 @@ class FlatBuckets:
             view.copy_(p.data)
             p.data = view
         self.grads_attached = False
+        # set by the fused optimizer step: the bucket's contents have been consumed, so the next backward
+        # OVERWRITES instead of accumulating (saves zeroing 13 GB per optimizer step)
+        self.consumed = False
 
     def is_current(self, named_params):
         sig = tuple((n, p.requires_grad, tuple(p.shape)) for n, p in named_params)
@@ -93,7 +96,7 @@ class FlatBuckets:
 
     def grads_live(self):
         """True when every trainable parameter's .grad is still our view (gradient accumulation in progress)."""
-        if not self.grads_attached:
+        if not self.grads_attached or self.consumed:
             return False
         gbase = self.grads.data_ptr()
         for n, p, o, k in self.entries:
@@ -109,6 +112,7 @@ class FlatBuckets:
                 continue
             p.grad = self.grads[o:o + k].view(p.shape)
         self.grads_attached = True
+        self.consumed = False
 
 
 class _StepFn(torch.autograd.Function):
@@ -136,8 +140,12 @@ class LlamaEngine:
         self._rope = {}
         self._saved = None
         self._ws = {}
+        # data-parallel overlap: called as hook(start_elem, end_elem) when a contiguous slice of the flat gradient
+        # bucket is final for this backward (set by the optimizer when world > 1; None = no overlap)
+        self.grad_ready_hook = None
         self.flags = None  # device int32[1]: splice validation bits (see llark_splice_scan)
         self.launches = 0  # kernels launched by the last forward(+backward): bench.py's gpu_launches
+        self.comm_chunk_layers = 4
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -376,6 +384,14 @@ class LlamaEngine:
             ops.rmsnorm_bwd(x, flat.pview(pfx + "input_layernorm.weight"), dxn1, rstd1, dx_mid, dx,
                             flat.gview(pfx + "input_layernorm.weight"), acc, ws_norm)
             n0 += 2
+            if self.grad_ready_hook is not None and l % self.comm_chunk_layers == 0:
+                # layers [l, hi) are final: their gradients form one contiguous slice of the bucket
+                lo_off = flat.offsets[f"model.layers.{l}.self_attn.q_proj.weight"][0]
+                hi_l = min(l + self.comm_chunk_layers, L)
+                hi_off = (flat.offsets[f"model.layers.{hi_l}.self_attn.q_proj.weight"][0] if hi_l < L
+                          else flat.offsets["model.norm.weight"][0])
+                if lo_off < flat.n_train and hi_off <= flat.n_train and hi_off > lo_off:
+                    self.grad_ready_hook(lo_off, hi_off)
 
         # splice + projector
         g_table = flat.gview("model.embed_tokens.weight", (V, H))

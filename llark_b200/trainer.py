@@ -96,7 +96,8 @@ class WrappedTrainer:
             step = self.state["global_step"]
             self.optimizer.param_groups[0]["lr"] = base_lr * cosine_with_warmup(step, max_steps, warmup)
             losses = []
-            for _ in range(accum):
+            for micro in range(accum):
+                self.optimizer.sync_gradients = micro == accum - 1  # DDP no_sync() on all but the last micro-batch
                 batch = next(it)
                 batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else
                              [t.to(dev, non_blocking=True) for t in v]) for k, v in batch.items()}

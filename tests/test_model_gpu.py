@@ -169,3 +169,34 @@ def test_llama7b_layer_shapes_run():
     for n in ("model.mm_projector.weight", "model.layers.0.mlp.down_proj.weight", "model.layers.0.self_attn.q_proj.weight",
               "model.norm.weight"):
         assert _rel(named[n].grad.float(), grads_o[n].float()) < 6e-2, n
+
+
+def test_optimizer_step_then_backward_overwrites_stale_grads(gold):
+    """After the fused optimizer step the gradient bucket is 'consumed': the next backward must overwrite it
+    (no stale accumulation), and the loss must go down on the same batch."""
+    from oracle import llama_oracle as lo
+    from llark_b200.optim import LlarkAdamW
+
+    cfg = lo.LlamaCfg(**gold["cfg"])
+    model = build_model(cfg, lo.init_params(cfg, seed=0))
+    opt = LlarkAdamW(model, lr=1e-3)
+    batch = _to_cuda(lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=0))
+    l0 = model(**batch).loss
+    l0.backward()
+    opt.step()
+    out = model(**batch)
+    out.loss.backward()
+    g_a = {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    model(**batch).loss.backward()
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad.float(), g_a[n]), n
+    assert out.loss.item() < l0.item()
+    # explicit zero_grad() between accumulation windows also works
+    opt.zero_grad()
+    model(**batch).loss.backward()
+    model(**batch).loss.backward()
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert _rel(p.grad.float(), 2 * g_a[n]) < 2e-2, n
