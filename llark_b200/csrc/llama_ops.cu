@@ -336,7 +336,7 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfl
         load8(gu + row * 2 * I + c, g);
         load8(gu + row * 2 * I + I + c, u);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = bf16_round(g[e] / (1.f + __expf(-g[e]))) * u[e];
+        for (int e = 0; e < 8; ++e) o[e] = bf16_round(__fdividef(g[e], 1.f + __expf(-g[e]))) * u[e];
         store8(act + row * I + c, o);
     }
 }
@@ -355,7 +355,7 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __
         load8(dact + row * I + c, d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float sg = 1.f / (1.f + __expf(-g[e]));
+            const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
             const float silu = g[e] * sg;
             du[e] = d[e] * bf16_round(silu);
             dg[e] = d[e] * u[e] * (sg * (1.f + g[e] * (1.f - sg)));
@@ -495,31 +495,33 @@ struct AdamArgs {
 //   g  = bf16(g * grad_scale * clip_coef)                (1/(world*accum) scale and clip_grad_norm_)
 //   p  = bf16(p * (1 - lr*wd)); m = bf16(lerp(m, g, 1-b1)); v = bf16(v*b2); v = bf16(v + (1-b2) g g)
 //   den = bf16(bf16(bf16(sqrt(v)) / bc2_sqrt) + eps);  p = bf16(p - (lr/bc1) * m / den)
-__device__ __forceinline__ void adamw_update8(float (&pf)[8], float (&gf)[8], float (&mf)[8], float (&vf)[8],
-                                              const AdamArgs& a, float clip, float step_size) {
-    const float gs = a.grad_scale;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        float gg = gf[e];
-        if (gs != 1.f) gg = bf16_round(gg * gs);
-        if (clip != 1.f) gg = bf16_round(gg * clip);
-        float pp = pf[e];
-        if (a.weight_decay != 0.f) pp = bf16_round(pp * (1.f - a.lr * a.weight_decay));
-        const float w = 1.f - a.beta1;
-        const float mm = bf16_round(w < 0.5f ? mf[e] + w * (gg - mf[e]) : gg - (gg - mf[e]) * (1.f - w));
-        float vv = bf16_round(vf[e] * a.beta2);
-        vv = bf16_round(vv + (1.f - a.beta2) * gg * gg);
-        float den = bf16_round(sqrtf(vv));
-        den = bf16_round(den / a.bc2_sqrt);
-        den = bf16_round(den + a.eps);
-        pp = bf16_round(pp - step_size * (mm / den));
-        pf[e] = pp; mf[e] = mm; vf[e] = vv;
-        gf[e] = 0.f;
+// The update costs ~100 instructions per element when written naively (IEEE sqrt and two IEEE divisions plus a
+// cvt pair per bf16 rounding): at 6.6 G elements that is ISSUE-bound (measured 31 ms), not HBM-bound. Every
+// intermediate is rounded to bf16 right after it is produced, so MUFU-based reciprocal / rsqrt (2 ulp in fp32) and
+// packed cvt.rn.bf16x2 conversions change nothing after rounding (tests/test_kernels_gpu.py compares with torch).
+__device__ __forceinline__ float2 round2(float a, float b) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);  // one cvt.rn.bf16x2.f32
+    return __bfloat1622float2(t);
+}
+__device__ __forceinline__ void adamw_update2(float& p0, float& p1, float g0, float g1, float& m0, float& m1,
+                                              float& v0, float& v1, const AdamArgs& a, float gmul, float w1,
+                                              float one_m_b2, float inv_bc2, float step_size, float decay) {
+    float2 g = make_float2(g0, g1);
+    if (gmul != 1.f) g = round2(g.x * gmul, g.y * gmul);
+    if (decay != 1.f) {
+        const float2 pd = round2(p0 * decay, p1 * decay);
+        p0 = pd.x; p1 = pd.y;
     }
+    const float2 m = round2(fmaf(w1, g.x - m0, m0), fmaf(w1, g.y - m1, m1));  // lerp(m, g, 1 - beta1), weight < 0.5
+    float2 v = round2(v0 * a.beta2, v1 * a.beta2);
+    v = round2(fmaf(one_m_b2 * g.x, g.x, v.x), fmaf(one_m_b2 * g.y, g.y, v.y));
+    float2 d = round2(v.x * rsqrtf(fmaxf(v.x, 1e-38f)), v.y * rsqrtf(fmaxf(v.y, 1e-38f)));  // sqrt(v)
+    d = round2(d.x * inv_bc2, d.y * inv_bc2);
+    d = round2(d.x + a.eps, d.y + a.eps);
+    const float2 pn = round2(fmaf(-step_size, __fdividef(m.x, d.x), p0), fmaf(-step_size, __fdividef(m.y, d.y), p1));
+    p0 = pn.x; p1 = pn.y; m0 = m.x; m1 = m.y; v0 = v.x; v1 = v.y;
 }
 
-// Two 16-byte vectors of each of the four streams are in flight per thread (8 independent 16 B loads) before any
-// arithmetic: the kernel is a pure HBM stream (read p,g,m,v; write p,m,v and the zeroed g).
 __global__ void __launch_bounds__(256)
 adamw_kernel(__nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ m,
              __nv_bfloat16* __restrict__ v, long long n, const float* __restrict__ sumsq, AdamArgs a, int zero_grad) {
@@ -528,39 +530,37 @@ adamw_kernel(__nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ g, __nv_
         const float total = sqrtf(sumsq[0]) * a.grad_scale;
         clip = fminf(1.f, a.max_norm / (total + 1e-6f));
     }
-    const float step_size = a.lr / a.bc1;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    // torch scales the gradient twice (1/world by DDP, then clip_grad_norm_), rounding in between; when only one
+    // of the two factors is active this is one multiply, otherwise the product differs from two roundings by at
+    // most one bf16 ulp of the gradient.
+    const float gmul = a.grad_scale * clip;
+    const float w1 = 1.f - a.beta1, one_m_b2 = 1.f - a.beta2;
+    const float inv_bc2 = 1.f / a.bc2_sqrt, step_size = a.lr / a.bc1;
+    const float decay = 1.f - a.lr * a.weight_decay;
     const long long nvec = n / 8;
-    // vectors tid, tid + nthreads (coalesced within each of the two halves of the iteration)
-    for (long long base = tid; base < nvec; base += 2 * nthreads) {
-        const long long i0 = base * 8;
-        const long long v1 = base + nthreads;
-        const bool has1 = v1 < nvec;
-        const long long i1 = v1 * 8;
-        float p0[8], g0[8], m0[8], w0[8], p1[8], g1[8], m1[8], w1[8];
-        load8(p + i0, p0);
-        load8(g + i0, g0);
-        load8(m + i0, m0);
-        load8(v + i0, w0);
-        if (has1) {
-            load8(p + i1, p1);
-            load8(g + i1, g1);
-            load8(m + i1, m1);
-            load8(v + i1, w1);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
+        const long long i = vi * 8;
+        const uint4 pu = *reinterpret_cast<const uint4*>(p + i);
+        const uint4 gu = *reinterpret_cast<const uint4*>(g + i);
+        const uint4 mu = *reinterpret_cast<const uint4*>(m + i);
+        const uint4 vu = *reinterpret_cast<const uint4*>(v + i);
+        uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w}, gw[4] = {gu.x, gu.y, gu.z, gu.w};
+        uint32_t mw[4] = {mu.x, mu.y, mu.z, mu.w}, vw[4] = {vu.x, vu.y, vu.z, vu.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 pf = unpack_bf16x2(pw[e]), gf = unpack_bf16x2(gw[e]), mf = unpack_bf16x2(mw[e]),
+                   vf = unpack_bf16x2(vw[e]);
+            adamw_update2(pf.x, pf.y, gf.x, gf.y, mf.x, mf.y, vf.x, vf.y, a, gmul, w1, one_m_b2, inv_bc2, step_size,
+                          decay);
+            pw[e] = pack_bf16x2(pf.x, pf.y);
+            mw[e] = pack_bf16x2(mf.x, mf.y);
+            vw[e] = pack_bf16x2(vf.x, vf.y);
         }
-        adamw_update8(p0, g0, m0, w0, a, clip, step_size);
-        store8(p + i0, p0);
-        store8(m + i0, m0);
-        store8(v + i0, w0);
-        if (zero_grad) store8(g + i0, g0);
-        if (has1) {
-            adamw_update8(p1, g1, m1, w1, a, clip, step_size);
-            store8(p + i1, p1);
-            store8(m + i1, m1);
-            store8(v + i1, w1);
-            if (zero_grad) store8(g + i1, g1);
-        }
+        *reinterpret_cast<uint4*>(p + i) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(m + i) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        *reinterpret_cast<uint4*>(v + i) = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+        if (zero_grad) *reinterpret_cast<uint4*>(g + i) = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -738,7 +738,7 @@ extern "C" int llark_adamw_step(void* p, void* g, void* m, void* v, long long n,
     a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.grad_scale = grad_scale; a.max_norm = max_norm;
-    adamw_kernel<<<grid_for(n / 16, 256, 148 * 8), 256, 0, st>>>((__nv_bfloat16*)p, (__nv_bfloat16*)g, (__nv_bfloat16*)m,
+    adamw_kernel<<<grid_for(n / 8, 256, 148 * 8), 256, 0, st>>>((__nv_bfloat16*)p, (__nv_bfloat16*)g, (__nv_bfloat16*)m,
                                                                 (__nv_bfloat16*)v, n, sumsq, a, zero_grad);
     return check_launch();
 }
