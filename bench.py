@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[2], named in `config.workload`): LLark Llama-2-7B + mm_projector training step on
 precomputed Jukebox embeddings -- random-init weights of the real architecture (H 4096, I 11008, 32 layers, 32
-heads, V 32004, projector 4800->4096), per-GPU micro-batch B samples of S = 512 tokens (header + <audio_start> +
+heads, V 32004, projector 4800->4096), per-GPU micro-batch B (default 16) samples of S = 512 tokens (header + <audio_start> +
 240 audio frames + <audio_end> + 256 random text ids; labels on the last 128 tokens), bf16 weights / grads / Adam
 states as the reference trains (m2t/train.py:101-103), lm_head frozen, text-embedding rows detached. One "step" =
 forward + backward + gradient all-reduce (N > 1) + global-norm clip + AdamW on one micro-batch per GPU.
@@ -49,9 +49,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="llark", choices=["llark", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU micro-batch (samples)")
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU micro-batch (samples)")
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers INVALIDATES the number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="llama", choices=["llama", "e2e"],
+                    help="llama = BASELINE configs[2] (precomputed Jukebox embeds, the default headline); "
+                         "e2e = configs[3]: 25 s waveform -> Jukebox front end -> projector -> Llama step in-process")
+    ap.add_argument("--jukebox-precision", default="bf16", choices=["bf16", "tf32"])
     return ap.parse_args()
 
 
@@ -264,18 +268,37 @@ def main():
 
     n_batches = 4
     host = [synth_batch(B, seed=1000 + rank + world * i) for i in range(n_batches)]
+    front = None
+    if args.workload == "e2e":
+        # configs[3]: the frozen Jukebox front end runs in the same process on the same GPU (no grad), its
+        # [B,240,4800] output replaces the precomputed encodings of the batch.
+        from llark_b200.jukebox import main as jm
+
+        _, vqvae, top_prior = jm.load_model("5b", precision=args.jukebox_precision)
+        g = torch.Generator().manual_seed(77 + rank)
+        for b in host:
+            b["waveform"] = torch.rand(B, 1102500, generator=g) * 2 - 1  # 25 s @ 44.1 kHz, mono
+            del b["audio_encodings"]
+
+        def front(batch):
+            with torch.no_grad():
+                enc = jm.embed_batch(batch["waveform"], vqvae, top_prior, pool_frames_per_second=10)
+            out = {k: v for k, v in batch.items() if k != "waveform"}
+            out["audio_encodings"] = enc
+            return out
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.cuda() for k, v in b.items()} for b in host]
 
     def step_resident(i):
-        out = model(**resident[i % n_batches])
+        b = resident[i % n_batches]
+        out = model(**(front(b) if front else b))
         out.loss.backward()
         opt.step()
         return out.loss
 
     def step_e2e(i):
         b = {k: v.cuda(non_blocking=True) for k, v in pinned[i % n_batches].items()}
-        out = model(**b)
+        out = model(**(front(b) if front else b))
         out.loss.backward()
         opt.step()
         return out.loss.item()  # D2H read of the step's result
@@ -352,8 +375,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[2]: LLark Llama-2-7B + mm_projector training step (fwd+bwd+clip+AdamW), "
-                               "precomputed Jukebox embeds [240,4800], seq 512, bf16",
+        "config": {"workload": ("configs[2]: LLark Llama-2-7B + mm_projector training step (fwd+bwd+clip+AdamW), "
+                                "precomputed Jukebox embeds [240,4800], seq 512, bf16") if front is None else
+                               ("configs[3]: end-to-end 25 s waveform -> Jukebox-5b front end (36-layer prior, "
+                                f"{args.jukebox_precision}) -> mm_projector -> Llama-2-7B training step, seq 512, bf16"),
                    "global_batch": B * world, "per_gpu_batch": B, "seq_len": SEQ, "layers": args.layers,
                    "parallelism": f"dp{world}", "l2": "working set (13.5 GB weights + activations) >> 126 MB L2; "
                                                      "4 rotating input batches",

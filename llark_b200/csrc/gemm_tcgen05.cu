@@ -374,8 +374,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ===================== TMA producer (both CTAs) =====================
+    // debug bit 16 (perf experiment): ONE producer thread issues both operands; default: warp 0 loads A and
+    // warp 3 loads B so the two TMA instructions of a stage are issued concurrently.
+    const bool split_prod = !(p.debug & 16);
+    if ((warp == 0 || (warp == 3 && split_prod)) && lane == 0) {
+        // ===================== TMA producers (both CTAs) =====================
+        const bool do_a = warp == 0, do_b = split_prod ? (warp == 3) : true;
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -388,44 +392,48 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
                 uint8_t* sb = sa + A_STAGE_BYTES;
                 const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
                 if (p.debug & 2) {
-                    if (leader) mbar_arrive(&full_bar[stage]);
+                    if (leader && do_a) mbar_arrive(&full_bar[stage]);
                     if (++stage == kStages2) {
                         stage = 0;
                         phase ^= 1;
                     }
                     continue;
                 }
-                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+                if (leader && do_a) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
                 const int k0 = kb * elems_per_row;
                 const int mn_per_box = 128 / p.elem_bytes;
                 const int box_bytes = elems_per_row * 128;
-                if (A_MN == 0) {
-                    if (p.debug & 1) {
-                        tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
-                        tma_load_2d_2sm(sa + 64 * 128, &tma_a, bar, k0, m0 + 64);
-                    } else
-                        tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
-                } else if (p.a_tma4 == 2) {
-                    tma_load_3d_2sm(sa, &tma_a, bar, 0, k0, m0 / mn_per_box);
-                } else if (p.a_tma4) {
-                    tma_load_4d_2sm(sa, &tma_a, bar, 0, 0, m0 / mn_per_box, k0 / 8);
-                } else {
-                    for (int j = 0; j < 128 / mn_per_box; ++j)
-                        tma_load_2d_2sm(sa + j * box_bytes, &tma_a, bar, m0 + j * mn_per_box, k0);
+                if (do_a) {
+                    if (A_MN == 0) {
+                        if (p.debug & 1) {
+                            tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                            tma_load_2d_2sm(sa + 64 * 128, &tma_a, bar, k0, m0 + 64);
+                        } else
+                            tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                    } else if (p.a_tma4 == 2) {
+                        tma_load_3d_2sm(sa, &tma_a, bar, 0, k0, m0 / mn_per_box);
+                    } else if (p.a_tma4) {
+                        tma_load_4d_2sm(sa, &tma_a, bar, 0, 0, m0 / mn_per_box, k0 / 8);
+                    } else {
+                        for (int j = 0; j < 128 / mn_per_box; ++j)
+                            tma_load_2d_2sm(sa + j * box_bytes, &tma_a, bar, m0 + j * mn_per_box, k0);
+                    }
                 }
-                if (B_MN == 0) {
-                    if (p.debug & 1) {
-                        tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
-                        tma_load_2d_2sm(sb + 64 * 128, &tma_b, bar, k0, n0 + 64);
-                    } else
-                        tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
-                } else if (p.b_tma4 == 2) {
-                    tma_load_3d_2sm(sb, &tma_b, bar, 0, k0, n0 / mn_per_box);
-                } else if (p.b_tma4) {
-                    tma_load_4d_2sm(sb, &tma_b, bar, 0, 0, n0 / mn_per_box, k0 / 8);
-                } else {
-                    for (int j = 0; j < 128 / mn_per_box; ++j)
-                        tma_load_2d_2sm(sb + j * box_bytes, &tma_b, bar, n0 + j * mn_per_box, k0);
+                if (do_b) {
+                    if (B_MN == 0) {
+                        if (p.debug & 1) {
+                            tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                            tma_load_2d_2sm(sb + 64 * 128, &tma_b, bar, k0, n0 + 64);
+                        } else
+                            tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                    } else if (p.b_tma4 == 2) {
+                        tma_load_3d_2sm(sb, &tma_b, bar, 0, k0, n0 / mn_per_box);
+                    } else if (p.b_tma4) {
+                        tma_load_4d_2sm(sb, &tma_b, bar, 0, 0, n0 / mn_per_box, k0 / 8);
+                    } else {
+                        for (int j = 0; j < 128 / mn_per_box; ++j)
+                            tma_load_2d_2sm(sb + j * box_bytes, &tma_b, bar, n0 + j * mn_per_box, k0);
+                    }
                 }
                 if (++stage == kStages2) {
                     stage = 0;
