@@ -6,6 +6,7 @@
 // earlier layers are still running.
 #include "common.cuh"
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace llark {
@@ -30,7 +31,17 @@ extern "C" int llark_comm_init(void** comm_out, const void* id128_host, int worl
     ncclUniqueId id;
     memcpy(&id, id128_host, sizeof(id));
     ncclComm_t comm;
-    ncclResult_t r = ncclCommInitRank(&comm, world, id, rank);
+    // The bucket all-reduce runs on a side stream UNDER the backward GEMMs (persistent, one CTA pair per TPC): every
+    // NCCL CTA takes an SM (and its TPC partner) away from them, and the reduction has ~250 ms of backward to hide
+    // behind, so it is capped to a few CTAs (LLARK_NCCL_MAX_CTAS, default 4) instead of NCCL's bandwidth-greedy default.
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    const char* e = getenv("LLARK_NCCL_MAX_CTAS");
+    const int max_ctas = e ? atoi(e) : 4;
+    if (max_ctas > 0) {
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = max_ctas;
+    }
+    ncclResult_t r = ncclCommInitRankConfig(&comm, world, id, rank, &cfg);
     if (r != ncclSuccess) {
         g_last_cuda_error = (int)r;
         return LLARK_ENCCL;

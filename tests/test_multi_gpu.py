@@ -27,15 +27,27 @@ def _worker(rank, world, port, q):
 
     cfg = lo.LlamaCfg()
     params = lo.init_params(cfg, seed=0)
-    model = build_model(cfg, params)
     comm = GradComm.from_torch_distributed()
-    opt = LlarkAdamW(model, lr=1e-2, max_grad_norm=1.0, comm=comm)
     batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=100 + rank)
+    # phase A: no overlap (the hooks are muted like DDP's no_sync), step() reduces the whole bucket
+    model = build_model(cfg, params)
+    opt = LlarkAdamW(model, lr=1e-2, max_grad_norm=1.0, comm=comm)
+    opt.sync_gradients = False
     out = model(**to_cuda(batch))
     out.loss.backward()
+    torch.cuda.synchronize()
     local = model.engine.flat.grads.float().clone()
+    opt.sync_gradients = True
     opt.step()
     new_params = model.engine.flat.params.float().cpu()
+    # phase B: slices are all-reduced on the side stream while backward is still running
+    model_b = build_model(cfg, params)
+    opt_b = LlarkAdamW(model_b, lr=1e-2, max_grad_norm=1.0, comm=comm)
+    model_b(**to_cuda(batch)).loss.backward()
+    assert opt_b._reduced, "overlap hooks did not fire"
+    opt_b.step()
+    overlapped = model_b.engine.flat.params.float().cpu()
+    assert torch.equal(overlapped, new_params), "overlapped and non-overlapped reductions must agree bit for bit"
     q.put((rank, local.cpu(), new_params, out.loss.item()))
     dist.barrier()
     comm.close()
