@@ -41,6 +41,8 @@ extern "C" int llark_comm_init(void** comm_out, const void* id128_host, int worl
         cfg.minCTAs = 1;
         cfg.maxCTAs = max_ctas;
     }
+    const char* pol = getenv("LLARK_NCCL_CTA_POLICY");  // 1 = NCCL_CTA_POLICY_EFFICIENCY (fewer CTAs, NCCL >= 2.27)
+    if (pol && atoi(pol) == 1) cfg.CTAPolicy = NCCL_CTA_POLICY_EFFICIENCY;
     ncclResult_t r = ncclCommInitRankConfig(&comm, world, id, rank, &cfg);
     if (r != ncclSuccess) {
         g_last_cuda_error = (int)r;

@@ -48,6 +48,7 @@ struct GemmParams {
     int num_m_blocks, num_n_blocks, num_k_blocks;
     int elem_bytes;  // 2 (bf16) or 4 (tf32)
     int a_tma4, b_tma4;  // MN-major operand loaded by ONE 4-D TMA box per stage (atom order: 64 MN, 8 K, chunks, K-groups)
+    int* tile_counter;   // CTA-pair kernel: dynamic tile scheduler counter (zero at launch, reset by the last fetch)
     int debug;       // LLARK_GEMM_DEBUG bits (perf experiments only): 1 = split K-major boxes in 64-row halves,
                      // 2 = producer issues no TMA (MMA runs on stale smem: isolates the UMMA rate)
 };
@@ -322,9 +323,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 // TMEM receives its 128 accumulator rows x 256 columns. Per SM the shared-memory traffic drops from
 // 96 (TMA writes) + 96 (UMMA reads) B/clk to 64 + 64 B/clk, which is what lets the tensor pipe stay busy.
 constexpr int kStages2 = 6;
+constexpr int kSched = 4;  // depth of the tile-index ring of the dynamic scheduler
 constexpr int B2_STAGE_BYTES = 128 * BLOCK_KB;  // this CTA's half of B: 16 KB
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;  // 32 KB per CTA per stage
-constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 512;
 
 template <int A_MN, int B_MN, int TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -336,7 +338,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + kStages2;
     uint64_t* tmem_full = empty_bar + kStages2;
     uint64_t* tmem_empty = tmem_full + kAccStages;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    uint64_t* sched_full = tmem_empty + kAccStages;   // [kSched] tile index published (one arrive per CTA)
+    uint64_t* sched_empty = sched_full + kSched;      // [kSched] leader's: all 13 consumers of the pair have read it
+    uint32_t* sched_tile = reinterpret_cast<uint32_t*>(sched_empty + kSched);  // [kSched]
+    uint32_t* tmem_base_slot = sched_tile + kSched;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -361,6 +366,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
         }
+        for (int i = 0; i < kSched; ++i) {
+            mbar_init(&sched_full[i], 1);
+            mbar_init(&sched_empty[i], 13);  // leader: A/B producers, MMA, 4 epilogue warps; peer: the same minus MMA
+        }
         mbar_fence_init();
         fence_proxy_async_smem();
     }
@@ -374,6 +383,53 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
+    // ---- dynamic tile scheduler ------------------------------------------------------------------------------
+    // Tiles are handed out by an atomic counter (one fetch per cluster per tile) instead of a static stride, so a
+    // cluster that cannot become resident (SMs taken by a concurrent NCCL kernel) does not sit on a share of the
+    // tiles. The leader's warp 2 publishes each index into BOTH CTAs' shared memory; every consumer role reads it,
+    // then arrives on the leader's sched_empty barrier. debug bit 32 = static stride (the old behaviour).
+    const bool dyn = !(p.debug & (32 | 16));
+    const uint32_t leader_sched_empty0 = mapa_shared(smem_u32(&sched_empty[0]), 0);
+    int s_slot = 0, s_static_tile = cluster_id;
+    uint32_t s_phase = 0;
+    auto next_tile = [&](bool whole_warp) -> int {
+        if (!dyn) {
+            const int t = s_static_tile;
+            s_static_tile += num_clusters;
+            return t < num_tiles ? t : -1;
+        }
+        mbar_wait_cluster(&sched_full[s_slot], s_phase);
+        const int t = (int)*reinterpret_cast<volatile uint32_t*>(&sched_tile[s_slot]);
+        if (whole_warp) __syncwarp();
+        if (!whole_warp || lane == 0) mbar_arrive_remote(leader_sched_empty0 + (uint32_t)s_slot * 8u);
+        if (++s_slot == kSched) {
+            s_slot = 0;
+            s_phase ^= 1;
+        }
+        return t;
+    };
+    if (dyn && warp == 2 && lane == 0 && leader) {
+        // ===================== tile scheduler (leader CTA) =====================
+        int slot = 0;
+        uint32_t phase = 0;
+        const uint32_t peer_full0 = mapa_shared(smem_u32(&sched_full[0]), 1);
+        const uint32_t peer_tile0 = mapa_shared(smem_u32(&sched_tile[0]), 1);
+        for (;;) {
+            mbar_wait_cluster(&sched_empty[slot], phase ^ 1);
+            int t = atomicAdd(p.tile_counter, 1);
+            if (t == num_tiles + num_clusters - 1) *p.tile_counter = 0;  // the very last fetch of this launch
+            if (t >= num_tiles) t = -1;
+            *reinterpret_cast<volatile uint32_t*>(&sched_tile[slot]) = (uint32_t)t;
+            st_shared_cluster_u32(peer_tile0 + (uint32_t)slot * 4u, (uint32_t)t);
+            mbar_arrive_remote(mapa_shared(smem_u32(&sched_full[slot]), 0));  // release.cluster, own CTA
+            mbar_arrive_remote(peer_full0 + (uint32_t)slot * 8u);
+            if (t < 0) break;
+            if (++slot == kSched) {
+                slot = 0;
+                phase ^= 1;
+            }
+        }
+    }
     // debug bit 16 (perf experiment): ONE producer thread issues both operands; default: warp 0 loads A and
     // warp 3 loads B so the two TMA instructions of a stage are issued concurrently.
     const bool split_prod = !(p.debug & 16);
@@ -382,7 +438,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const bool do_a = warp == 0, do_b = split_prod ? (warp == 3) : true;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int tile = next_tile(false); tile >= 0; tile = next_tile(false)) {
             const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
             const int m0 = tc.m_blk * 256 + (int)rank * 128;
             const int n0 = tc.n_blk * BLOCK_N + (int)rank * 128;
@@ -464,7 +520,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        for (int tile = next_tile(false); tile >= 0; tile = next_tile(false), ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -499,7 +555,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int ew = warp - 4;
         int it = 0;
         const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        for (int tile = next_tile(true); tile >= 0; tile = next_tile(true), ++it) {
             const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
@@ -729,6 +785,18 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     return LLARK_OK;
 }
 
+static int* g_tile_counters = nullptr;  // ring of zero-initialised device counters for the dynamic scheduler
+static unsigned g_counter_seq = 0;
+static int* next_tile_counter() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_tile_counters) {
+        if (cudaMalloc(&g_tile_counters, 4096 * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(g_tile_counters, 0, 4096 * sizeof(int));
+        cudaDeviceSynchronize();  // one-time: the zeroed ring must be visible to launches on any stream
+    }
+    return g_tile_counters + (g_counter_seq++ % 4096);
+}
+
 static int g_gemm_mode = -1;  // -1: read LLARK_GEMM_2CTA from the environment on first use; 0: 1-CTA; 1: CTA pair
 
 }  // namespace llark
@@ -808,6 +876,11 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
     p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     p.num_k_blocks = (K + epr - 1) / epr;
     p.elem_bytes = eb;
+    p.tile_counter = nullptr;
+    if (two_cta) {
+        p.tile_counter = next_tile_counter();
+        if (!p.tile_counter) return LLARK_ECUDA;
+    }
     p.a_tma4 = a4 ? use4 : 0;
     p.b_tma4 = b4 ? use4 : 0;
     {
