@@ -8,11 +8,14 @@
 // exp2 with pre-scaled log2e). Attention is 1 % of step FLOPs at S = 512; the tcgen05/TMEM
 // version is a later-round upgrade and DESIGN.md says so.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/llark_b200.h"
 
 namespace llark {
 
 extern thread_local int g_last_cuda_error;
+int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
+                       float scale, cudaStream_t st);  // attention_tc.cu
 
 constexpr int HD = 128;        // head dim
 constexpr int LDS = HD + 8;    // padded smem row (272 B): conflict-free ldmatrix
@@ -553,6 +556,17 @@ using namespace llark;
 extern "C" int llark_attn_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S,
                               int n_heads, int head_dim, float scale, cudaStream_t st) {
     if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0) return LLARK_EINVAL;
+    // LLARK_ATTN_TC=1 selects the tcgen05/TMEM kernel (attention_tc.cu) for S <= 4096; default (until it has been
+    // validated on a B200) is the mma.sync kernel below
+    static int use_tc = -1;
+    if (use_tc < 0) {
+        const char* e = getenv("LLARK_ATTN_TC");
+        use_tc = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (use_tc) {
+        const int rc_tc = attn_fwd_tc_launch(qkv, key_mask, out, lse, B, S, n_heads, scale, st);
+        if (rc_tc != LLARK_EINVAL) return rc_tc;
+    }
     int rc = set_smem((const void*)attn_fwd_kernel, FWD_SMEM);
     if (rc) return rc;
     dim3 grid((S + 63) / 64, n_heads, B);

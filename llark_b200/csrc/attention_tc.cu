@@ -1,0 +1,384 @@
+// Causal self-attention FORWARD on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), head_dim 128.
+// Replaces the eager/SDPA attention inside transformers' LlamaAttention reached at m2t/models/llamav2.py:224 (the
+// same contract as attention.cu's mma.sync kernel, which remains the path for S > 4096 and the backward pass).
+//
+// One CTA = one (batch, head, 128-query tile); 192 threads, two CTAs resident per SM (99 KB smem, 256 TMEM columns
+// each) so one CTA's softmax overlaps the other's MMAs:
+//   warp 0 (one lane) : TMA producer. Q tile once (4 boxes of 64 rows x 128 B), then the K / V tiles of 64 keys in the
+//                       order the MMA warp consumes them (K0, K1, V0, K2, V1, ...) through a 3-slot 16 KB ring.
+//   warp 1            : TMEM allocator; one lane issues tcgen05.mma:
+//                         S[j&1] (128 x 64 fp32, TMEM)  = Q (K-major smem) . K_j^T (K-major smem)       8 x K16
+//                         O      (128 x 128 fp32, TMEM) += P_j (K-major smem, bf16) . V_j (MN-major smem) 4 x K16
+//                       S is double-buffered so Q.K_{j+1}^T runs while the softmax warps work on S_j.
+//   warps 2-5         : softmax, one query row per thread (TMEM lane == row): tcgen05.ld S -> scale, causal and
+//                       key-padding mask -> running max / sum (exp2 domain) -> bf16 P written to shared memory in the
+//                       128-byte-swizzled K-major layout the UMMA descriptor expects. When a row's running max moved,
+//                       the O accumulator is rescaled in TMEM (tcgen05.ld / tcgen05.st) before P.V_j is issued.
+//                       Epilogue: O / l -> bf16, LSE (natural log, +inf for a fully masked row).
+#include "common.cuh"
+#include "../../include/llark_b200.h"
+#include <cuda.h>
+
+namespace llark {
+
+extern thread_local int g_last_cuda_error;
+int tensor_map_2d(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
+                  int box_outer, int elem_bytes);  // gemm_tcgen05.cu (cached cuTensorMapEncodeTiled, 128 B swizzle)
+
+namespace atc {
+
+constexpr int HD = 128;
+constexpr int BQ = 128;         // query rows per CTA
+constexpr int BK = 64;          // keys per tile
+constexpr int kThreads = 192;
+constexpr int kSlots = 3;       // K/V ring
+constexpr int Q_BYTES = BQ * HD * 2;        // 32 KB: 2 d-chunks x 128 rows x 128 B
+constexpr int KV_BYTES = BK * HD * 2;       // 16 KB: 2 d-chunks x 64 rows x 128 B
+constexpr int P_BYTES = BQ * BK * 2;        // 16 KB: 128 rows x 128 B
+constexpr int MAX_S = 4096;                 // key-mask bit words kept in shared memory
+constexpr int OFF_KV = Q_BYTES;
+constexpr int OFF_P = OFF_KV + kSlots * KV_BYTES;
+constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int OFF_MASK = OFF_BAR + 128;
+constexpr int SMEM_BYTES = OFF_MASK + (MAX_S / 32) * 4 + 1024 /*alignment slack*/;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void softmax_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct Ring {
+    int slot = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++slot == kSlots) {
+            slot = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned char* __restrict__ mask,
+                   __nv_bfloat16* __restrict__ O, float* __restrict__ lse_out, int S, int NH, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + OFF_KV;
+    uint8_t* sP = smem + OFF_P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* q_full = bars;              // [1]
+    uint64_t* kv_full = bars + 1;         // [kSlots]
+    uint64_t* kv_empty = kv_full + kSlots;  // [kSlots]
+    uint64_t* s_full = kv_empty + kSlots;   // [2]
+    uint64_t* s_empty = s_full + 2;         // [2]
+    uint64_t* p_full = s_empty + 2;         // [1]
+    uint64_t* pv_done = p_full + 1;         // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint32_t* maskw = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = gridDim.x - 1 - blockIdx.x;  // longest rows first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * BQ;
+    const int n_key_tiles = (S + BK - 1) / BK;
+    const int n_kv = min(n_key_tiles, (q0 + BQ) / BK);  // causal: keys <= q0 + 127
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 4);
+        }
+        mbar_init(p_full, 4);
+        mbar_init(pv_done, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_O = tmem_base + 128;  // columns [128, 256); S buffers at [0, 64) and [64, 128)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            const int row0 = b * S;
+            const int cq = h * HD, ck = NH * HD + h * HD, cv = 2 * NH * HD + h * HD;
+            mbar_arrive_expect_tx(q_full, Q_BYTES);
+            for (int c = 0; c < 2; ++c)
+                for (int rh = 0; rh < 2; ++rh)
+                    tma_load_2d(sQ + c * (BQ * 128) + rh * (64 * 128), &tm_qkv, q_full, cq + c * 64, row0 + q0 + rh * 64);
+            Ring r;
+            auto load_tile = [&](int col, int j) {
+                mbar_wait(&kv_empty[r.slot], r.phase ^ 1);
+                uint8_t* dst = sKV + r.slot * KV_BYTES;
+                mbar_arrive_expect_tx(&kv_full[r.slot], KV_BYTES);
+                tma_load_2d(dst, &tm_qkv, &kv_full[r.slot], col, row0 + j * BK);
+                tma_load_2d(dst + BK * 128, &tm_qkv, &kv_full[r.slot], col + 64, row0 + j * BK);
+                r.advance();
+            };
+            load_tile(ck, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) load_tile(ck, j + 1);
+                load_tile(cv, j);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            // instruction descriptors: F32 accumulate, bf16 operands; S: M128 N64, both K-major;
+            // PV: M128 N128, A (P) K-major, B (V, stored [key][d]) MN-major
+            const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BK >> 3) << 17) |
+                                     ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) |
+                                      ((uint32_t)(BQ >> 4) << 24);
+            const uint64_t qdesc0 = make_desc(smem_u32(sQ), 0, 1024);
+            const uint64_t qdesc1 = make_desc(smem_u32(sQ + BQ * 128), 0, 1024);
+            const uint64_t pdesc = make_desc(smem_u32(sP), 0, 1024);
+            Ring r;
+            auto issue_s = [&](int j) {
+                const int sb = j & 1;
+                mbar_wait(&s_empty[sb], ((uint32_t)(j >> 1) & 1) ^ 1);
+                mbar_wait(&kv_full[r.slot], r.phase);
+                tc_fence_after();
+                const uint32_t kaddr = smem_u32(sKV + r.slot * KV_BYTES);
+                const uint64_t kdesc0 = make_desc(kaddr, 0, 1024);
+                const uint64_t kdesc1 = make_desc(kaddr + BK * 128, 0, 1024);
+                const uint32_t tS = tmem_base + sb * BK;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t ad = (k < 4 ? qdesc0 : qdesc1) + (uint64_t)((k & 3) * 2);
+                    const uint64_t bd = (k < 4 ? kdesc0 : kdesc1) + (uint64_t)((k & 3) * 2);
+                    umma_f16(tS, ad, bd, idesc_s, k != 0);
+                }
+                umma_commit(&kv_empty[r.slot]);
+                umma_commit(&s_full[sb]);
+                r.advance();
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_s(j + 1);
+                mbar_wait(&kv_full[r.slot], r.phase);
+                mbar_wait(p_full, (uint32_t)j & 1);
+                tc_fence_after();
+                const uint64_t vdesc = make_desc(smem_u32(sKV + r.slot * KV_BYTES), BK * 128, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tmem_O, pdesc + (uint64_t)(k * 2), vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) != 0);
+                umma_commit(&kv_empty[r.slot]);
+                umma_commit(pv_done);
+                r.advance();
+            }
+        }
+    } else {
+        // ===================== softmax / epilogue (warps 2-5) =====================
+        const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+        const int r_in = quad * 32 + lane;     // row inside the query tile == TMEM lane
+        const int qi = q0 + r_in;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // key-padding mask -> one bit per key
+        {
+            const int sw = warp - 2;
+            const int nwords = n_key_tiles * 2;
+            for (int w = sw; w < nwords; w += 4) {
+                const int key = w * 32 + lane;
+                const bool ok = key < S && (!mask || mask[(long long)b * S + key] != 0);
+                const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) maskw[w] = bits;
+            }
+            softmax_group_sync();
+        }
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            const int sb = j & 1;
+            mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[2][32];
+            tmem_ld_32x32b_x32(lane_base + sb * BK, sv[0]);
+            tmem_ld_32x32b_x32(lane_base + sb * BK + 32, sv[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[sb]);
+
+            const int k0 = j * BK;
+            const uint32_t mw0 = maskw[2 * j], mw1 = maskw[2 * j + 1];
+            const bool plain = (k0 + BK - 1 <= q0 + quad * 32) && mw0 == 0xffffffffu && mw1 == 0xffffffffu;  // warp-uniform
+            float rmax = -INFINITY;
+            if (plain) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = __uint_as_float(sv[hh][c]) * scale_log2;
+                        sv[hh][c] = __float_as_uint(v);
+                        rmax = fmaxf(rmax, v);
+                    }
+            } else {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t mw = hh ? mw1 : mw0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int key = k0 + hh * 32 + c;
+                        const bool ok = key <= qi && ((mw >> c) & 1u);
+                        const float v = ok ? __uint_as_float(sv[hh][c]) * scale_log2 : -INFINITY;
+                        sv[hh][c] = __float_as_uint(v);
+                        rmax = fmaxf(rmax, v);
+                    }
+                }
+            }
+            const float m_new = fmaxf(m_run, rmax);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = ex2(m_run - m_use);
+            m_run = m_new;
+            float psum = 0.f;
+            uint32_t pk[32];  // 64 bf16 probabilities
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = ex2(__uint_as_float(sv[hh][c]) - m_use);
+                    const float p1 = ex2(__uint_as_float(sv[hh][c + 1]) - m_use);
+                    psum += p0 + p1;
+                    pk[hh * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
+                }
+            l_run = l_run * alpha + psum;
+
+            if (j > 0) {
+                // P.V_{j-1} must have retired: sP is free again and O holds tiles 0..j-1
+                mbar_wait(pv_done, (uint32_t)(j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32b_x32(lane_base + 128 + c * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                        tmem_st_32x32b_x32(lane_base + 128 + c * 32, ov);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // P row -> shared memory, K-major 128 B rows, 16-byte units XOR-swizzled by (row & 7)
+            {
+                uint8_t* prow = sP + r_in * 128;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint4 val = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    *reinterpret_cast<uint4*>(prow + ((u ^ (r_in & 7)) << 4)) = val;
+                }
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // epilogue: O / l -> bf16
+        mbar_wait(pv_done, (uint32_t)(n_kv - 1) & 1);
+        tc_fence_after();
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        const bool row_ok = qi < S;
+        __nv_bfloat16* optr = O + ((long long)b * S + qi) * ((long long)NH * HD) + (long long)h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(lane_base + 128 + c * 32, ov);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(ov[8 * u]) * inv, __uint_as_float(ov[8 * u + 1]) * inv);
+                    o.y = pack_bf16x2(__uint_as_float(ov[8 * u + 2]) * inv, __uint_as_float(ov[8 * u + 3]) * inv);
+                    o.z = pack_bf16x2(__uint_as_float(ov[8 * u + 4]) * inv, __uint_as_float(ov[8 * u + 5]) * inv);
+                    o.w = pack_bf16x2(__uint_as_float(ov[8 * u + 6]) * inv, __uint_as_float(ov[8 * u + 7]) * inv);
+                    *reinterpret_cast<uint4*>(optr + c * 32 + u * 8) = o;
+                }
+            }
+        }
+        if (row_ok)
+            lse_out[((long long)b * NH + h) * S + qi] = l_run > 0.f ? m_run * LN2 + logf(l_run) : INFINITY;
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace atc
+
+// Returns LLARK_OK when the tcgen05 kernel was launched, LLARK_EINVAL when the shape is outside its envelope
+// (the caller then uses the mma.sync kernel).
+int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
+                       float scale, cudaStream_t st) {
+    using namespace atc;
+    if (S > MAX_S || (long long)B * S > 0x7fffffffLL) return LLARK_EINVAL;
+    CUtensorMap tm;
+    const long long ld = 3LL * n_heads * HD;
+    int rc = tensor_map_2d(&tm, qkv, ld, (long long)B * S, ld, 64, 64, 2);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            g_last_cuda_error = (int)e;
+            return LLARK_ECUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, n_heads, B);
+    attn_fwd_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tm, key_mask, (__nv_bfloat16*)out, lse, S, n_heads,
+                                                           scale * LOG2E);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_ECUDA;
+    }
+    return LLARK_OK;
+}
+
+}  // namespace llark

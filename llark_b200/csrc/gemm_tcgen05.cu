@@ -666,6 +666,14 @@ static int get_tensor_map(CUtensorMap* out, const void* ptr, long long inner, lo
     return LLARK_OK;
 }
 
+// Exported to the other translation units of the library (attention_tc.cu): cached 2-D tiled map, 128 B swizzle.
+int tensor_map_2d(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
+                  int box_outer, int elem_bytes) {
+    int rc = ensure_driver();
+    if (rc) return rc;
+    return get_tensor_map(out, ptr, inner, outer, ld, box_inner, box_outer, elem_bytes);
+}
+
 // 4-D tensor map over a row-major [K][ld] array ([K][MN] valid, MN contiguous) that delivers a whole MN-major
 // operand stage with ONE box: dims (128 B of MN, 8 K rows, MN chunks, K groups of 8), box (.., 8, chunks, kgroups).
 static int get_tensor_map_mn4(CUtensorMap* out, const void* ptr, long long mn, long long k, long long ld, int chunks,
