@@ -16,6 +16,19 @@ namespace llark {
 extern thread_local int g_last_cuda_error;
 int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
                        float scale, cudaStream_t st);  // attention_tc.cu
+int attn_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
+                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, cudaStream_t st);
+// LLARK_ATTN_TC bit 0: tcgen05 forward, bit 1: tcgen05 backward. Default 3 (both, validated on B200: same test
+// tolerances as the mma.sync kernels, forward 202 -> 89 us and backward 717 -> 481 us at B 16, S 512, 32 heads);
+// 0 selects the mma.sync kernels of this file (also used for S > 4096).
+static int attn_tc_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("LLARK_ATTN_TC");
+        mode = e ? atoi(e) & 3 : 3;
+    }
+    return mode;
+}
 
 constexpr int HD = 128;        // head dim
 constexpr int LDS = HD + 8;    // padded smem row (272 B): conflict-free ldmatrix
@@ -556,14 +569,8 @@ using namespace llark;
 extern "C" int llark_attn_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S,
                               int n_heads, int head_dim, float scale, cudaStream_t st) {
     if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0) return LLARK_EINVAL;
-    // LLARK_ATTN_TC=1 selects the tcgen05/TMEM kernel (attention_tc.cu) for S <= 4096; default (until it has been
-    // validated on a B200) is the mma.sync kernel below
-    static int use_tc = -1;
-    if (use_tc < 0) {
-        const char* e = getenv("LLARK_ATTN_TC");
-        use_tc = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    if (use_tc) {
+    // default: the tcgen05/TMEM kernel (attention_tc.cu) for S <= 4096
+    if (attn_tc_mode() & 1) {
         const int rc_tc = attn_fwd_tc_launch(qkv, key_mask, out, lse, B, S, n_heads, scale, st);
         if (rc_tc != LLARK_EINVAL) return rc_tc;
     }
@@ -590,6 +597,10 @@ extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, co
                                                                                 n_heads);
     int rc = check_launch2();
     if (rc) return rc;
+    if (attn_tc_mode() & 2) {
+        const int rc_tc = attn_bwd_tc_launch(qkv, key_mask, dout, lse, Dsum, dqkv, B, S, n_heads, scale, st);
+        if (rc_tc != LLARK_EINVAL) return rc_tc;
+    }
     rc = set_smem((const void*)attn_bwd_dkdv_kernel, DKDV_SMEM);
     if (rc) return rc;
     rc = set_smem((const void*)attn_bwd_dq_kernel, DQ_SMEM);

@@ -1,7 +1,9 @@
-// Causal self-attention FORWARD on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), head_dim 128.
-// Replaces the eager/SDPA attention inside transformers' LlamaAttention reached at m2t/models/llamav2.py:224 (the
-// same contract as attention.cu's mma.sync kernel, which remains the path for S > 4096 and the backward pass).
+// Causal self-attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), head_dim 128: forward kernel
+// first, the two backward kernels further down.
+// Replaces the eager/SDPA attention inside transformers' LlamaAttention reached at m2t/models/llamav2.py:224 and its
+// autograd backward (the same contract as attention.cu's mma.sync kernels, which remain the path for S > 4096).
 //
+// FORWARD
 // One CTA = one (batch, head, 128-query tile); 192 threads, two CTAs resident per SM (99 KB smem, 256 TMEM columns
 // each) so one CTA's softmax overlaps the other's MMAs:
 //   warp 0 (one lane) : TMA producer. Q tile once (4 boxes of 64 rows x 128 B), then the K / V tiles of 64 keys in the
@@ -241,16 +243,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
             const int k0 = j * BK;
             const uint32_t mw0 = maskw[2 * j], mw1 = maskw[2 * j + 1];
             const bool plain = (k0 + BK - 1 <= q0 + quad * 32) && mw0 == 0xffffffffu && mw1 == 0xffffffffu;  // warp-uniform
+            // row max of the RAW scores (scale > 0, so the max commutes with the scaling); masked entries -> -inf
             float rmax = -INFINITY;
             if (plain) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = __uint_as_float(sv[hh][c]) * scale_log2;
-                        sv[hh][c] = __float_as_uint(v);
-                        rmax = fmaxf(rmax, v);
-                    }
+                    for (int c = 0; c < 32; ++c) rmax = fmaxf(rmax, __uint_as_float(sv[hh][c]));
             } else {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -259,13 +258,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
                     for (int c = 0; c < 32; ++c) {
                         const int key = k0 + hh * 32 + c;
                         const bool ok = key <= qi && ((mw >> c) & 1u);
-                        const float v = ok ? __uint_as_float(sv[hh][c]) * scale_log2 : -INFINITY;
+                        const float v = ok ? __uint_as_float(sv[hh][c]) : -INFINITY;
                         sv[hh][c] = __float_as_uint(v);
                         rmax = fmaxf(rmax, v);
                     }
                 }
             }
-            const float m_new = fmaxf(m_run, rmax);
+            // Lazy rescaling: the reference maximum m_run only moves when the true maximum has grown by more than
+            // 2^8 (probabilities then stay <= 256, exact enough in bf16 / fp32), so the TMEM round trip that rescales
+            // O is rare after the first tile. O / l and LSE = m*ln2 + log(l) are invariant to the choice of m_run.
+            const float m_cand = fmaxf(m_run, rmax * scale_log2);
+            const bool move = (m_cand > m_run + 8.f) || (m_run == -INFINITY);
+            const float m_new = move ? m_cand : m_run;
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
             const float alpha = ex2(m_run - m_use);
             m_run = m_new;
@@ -275,8 +279,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
             for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
-                    const float p0 = ex2(__uint_as_float(sv[hh][c]) - m_use);
-                    const float p1 = ex2(__uint_as_float(sv[hh][c + 1]) - m_use);
+                    const float p0 = ex2(fmaf(__uint_as_float(sv[hh][c]), scale_log2, -m_use));
+                    const float p1 = ex2(fmaf(__uint_as_float(sv[hh][c + 1]), scale_log2, -m_use));
                     psum += p0 + p1;
                     pk[hh * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
                 }
@@ -349,6 +353,462 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
     }
 }
 
+
+// =====================================================================================================================
+// BACKWARD on tcgen05. Two kernels with the forward kernel's structure and exactly its two MMA forms
+//   "KK": D[128 x 64]  = A[128 rows, K-major, d in 2 chunks] . B[64 rows, K-major]^T            (8 x K16)
+//   "PV": D[128 x 128] += A[128 rows x 64, K-major, written by threads] . B[64 K-rows x 128, MN-major]  (4 x K16)
+// so no operand is ever transposed in memory:
+//   dQ kernel   (CTA = 128 queries, streams 64-key tiles):  S = Q K^T, dP = dO V^T (KK); dS = P o (dP - D);
+//                                                           dQ += dS K (PV, K_j read MN-major)
+//   dK/dV kernel (CTA = 128 keys, streams 64-query tiles):  S^T = K Q^T, dP^T = V dO^T (KK); P^T, dS^T;
+//                                                           dV += P^T dO, dK += dS^T Q (PV, dO_i / Q_i read MN-major)
+// P is recomputed from the saved LSE (p = exp2(s*scale*log2e - lse*log2e)), D = rowsum(dO o O) comes from
+// attn_bwd_prep_kernel (attention.cu). 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = two compute warpgroups that split the 64 columns of every S / dP row (no row reductions are needed in
+// the backward pass, so the split is free). S and dP are double-buffered in TMEM: the KK MMAs of tile t+1 run while
+// the compute warps work on tile t. One CTA per SM (145-162 KB of shared memory, all 512 TMEM columns).
+constexpr int kBwdThreads = 320;
+constexpr int RING_SLOTS = 4;
+
+__device__ __forceinline__ void mma_kk_128x64(uint32_t tD, uint32_t a_addr, uint32_t a_chunk_bytes, uint32_t b_addr,
+                                              uint32_t b_chunk_bytes, uint32_t idesc) {
+    const uint64_t a0 = make_desc(a_addr, 0, 1024), a1 = make_desc(a_addr + a_chunk_bytes, 0, 1024);
+    const uint64_t b0 = make_desc(b_addr, 0, 1024), b1 = make_desc(b_addr + b_chunk_bytes, 0, 1024);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        umma_f16(tD, (k < 4 ? a0 : a1) + (uint64_t)((k & 3) * 2), (k < 4 ? b0 : b1) + (uint64_t)((k & 3) * 2), idesc,
+                 k != 0);
+}
+__device__ __forceinline__ void mma_pv_128x128(uint32_t tD, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+                                               bool accumulate) {
+    const uint64_t ad = make_desc(a_addr, 0, 1024);
+    const uint64_t bd = make_desc(b_addr, BK * 128, 1024);  // MN-major: the two 64-wide N chunks are 8 KB apart
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        umma_f16(tD, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 128), idesc, accumulate || k != 0);
+}
+__device__ __forceinline__ void compute_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// 32 fp32 values -> 32 bf16 -> four 16-byte units (g*4 .. g*4+3) of row r of a 128-byte-row, XOR-swizzled tile
+__device__ __forceinline__ void store_half_row(uint8_t* tile, int r, int g, const float (&v)[32]) {
+    uint8_t* row = tile + r * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = pack_bf16x2(v[8 * u], v[8 * u + 1]);
+        w.y = pack_bf16x2(v[8 * u + 2], v[8 * u + 3]);
+        w.z = pack_bf16x2(v[8 * u + 4], v[8 * u + 5]);
+        w.w = pack_bf16x2(v[8 * u + 6], v[8 * u + 7]);
+        *reinterpret_cast<uint4*>(row + (((g * 4 + u) ^ (r & 7)) << 4)) = w;
+    }
+}
+// 64 fp32 accumulator columns of this thread's TMEM lane -> scaled bf16 -> 128 contiguous bytes in global memory
+__device__ __forceinline__ void store_acc_64(uint32_t taddr, __nv_bfloat16* dst, float mul, bool ok) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, ov);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(ov[8 * u]) * mul, __uint_as_float(ov[8 * u + 1]) * mul);
+                o.y = pack_bf16x2(__uint_as_float(ov[8 * u + 2]) * mul, __uint_as_float(ov[8 * u + 3]) * mul);
+                o.z = pack_bf16x2(__uint_as_float(ov[8 * u + 4]) * mul, __uint_as_float(ov[8 * u + 5]) * mul);
+                o.w = pack_bf16x2(__uint_as_float(ov[8 * u + 6]) * mul, __uint_as_float(ov[8 * u + 7]) * mul);
+                *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = o;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- dQ
+constexpr int DQ_OFF_DO = Q_BYTES;
+constexpr int DQ_OFF_RING = 2 * Q_BYTES;
+constexpr int DQ_OFF_DS = DQ_OFF_RING + RING_SLOTS * KV_BYTES;
+constexpr int DQ_OFF_BAR = DQ_OFF_DS + P_BYTES;
+constexpr int DQ_OFF_MASK = DQ_OFF_BAR + 256;
+constexpr int DQ_SMEM_BYTES = DQ_OFF_MASK + (MAX_S / 32) * 4 + 1024;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                      const unsigned char* __restrict__ mask, const float* __restrict__ lse,
+                      const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
+                      float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sdO = smem + DQ_OFF_DO;
+    uint8_t* sRing = smem + DQ_OFF_RING;
+    uint8_t* sdS = smem + DQ_OFF_DS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_OFF_BAR);
+    uint64_t* q_full = bars;                       // [1]  Q and dO tiles landed
+    uint64_t* ring_full = bars + 1;                // [4]
+    uint64_t* ring_empty = ring_full + RING_SLOTS; // [4]
+    uint64_t* sdp_full = ring_empty + RING_SLOTS;  // [2]  S and dP of tile j are in TMEM
+    uint64_t* sdp_empty = sdp_full + 2;            // [2]  8 compute warps have read them
+    uint64_t* ds_full = sdp_empty + 2;             // [1]  dS tile written to shared memory
+    uint64_t* dq_done = ds_full + 1;               // [1]  dQ += dS K_j retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 1);
+    uint32_t* maskw = reinterpret_cast<uint32_t*>(smem + DQ_OFF_MASK);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = gridDim.x - 1 - blockIdx.x;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qt * BQ;
+    const int n_key_tiles = (S + BK - 1) / BK;
+    const int n_kv = min(n_key_tiles, (q0 + BQ) / BK);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < RING_SLOTS; ++i) {
+            mbar_init(&ring_full[i], 1);
+            mbar_init(&ring_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sdp_full[i], 1);
+            mbar_init(&sdp_empty[i], 8);
+        }
+        mbar_init(ds_full, 8);
+        mbar_init(dq_done, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;  // S[2] @ 0,64   dP[2] @ 128,192   dQ @ 256..383
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int row0 = b * S;
+            const int cq = h * HD, ck = NH * HD + h * HD, cv = 2 * NH * HD + h * HD;
+            mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
+            for (int c = 0; c < 2; ++c)
+                for (int rh = 0; rh < 2; ++rh) {
+                    tma_load_2d(sQ + c * (BQ * 128) + rh * (64 * 128), &tm_qkv, q_full, cq + c * 64, row0 + q0 + rh * 64);
+                    tma_load_2d(sdO + c * (BQ * 128) + rh * (64 * 128), &tm_do, q_full, cq + c * 64, row0 + q0 + rh * 64);
+                }
+            for (int j = 0; j < n_kv; ++j) {
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv) {
+                    const int it = 2 * j + kv, slot = it & 3;
+                    mbar_wait(&ring_empty[slot], (((uint32_t)it >> 2) & 1) ^ 1);
+                    uint8_t* dst = sRing + slot * KV_BYTES;
+                    mbar_arrive_expect_tx(&ring_full[slot], KV_BYTES);
+                    const int col = kv ? cv : ck;
+                    tma_load_2d(dst, &tm_qkv, &ring_full[slot], col, row0 + j * BK);
+                    tma_load_2d(dst + BK * 128, &tm_qkv, &ring_full[slot], col + 64, row0 + j * BK);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_kk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BK >> 3) << 17) |
+                                      ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) |
+                                      ((uint32_t)(BQ >> 4) << 24);
+            auto issue_sdp = [&](int j) {
+                const int sb = j & 1;
+                const int itk = 2 * j, itv = 2 * j + 1;
+                mbar_wait(&sdp_empty[sb], ((uint32_t)(j >> 1) & 1) ^ 1);
+                mbar_wait(&ring_full[itk & 3], ((uint32_t)itk >> 2) & 1);
+                tc_fence_after();
+                mma_kk_128x64(tmem_base + sb * BK, smem_u32(sQ), BQ * 128, smem_u32(sRing + (itk & 3) * KV_BYTES),
+                              BK * 128, idesc_kk);
+                mbar_wait(&ring_full[itv & 3], ((uint32_t)itv >> 2) & 1);
+                tc_fence_after();
+                mma_kk_128x64(tmem_base + 128 + sb * BK, smem_u32(sdO), BQ * 128,
+                              smem_u32(sRing + (itv & 3) * KV_BYTES), BK * 128, idesc_kk);
+                umma_commit(&ring_empty[itv & 3]);  // V_j is not needed again
+                umma_commit(&sdp_full[sb]);
+            };
+            mbar_wait(q_full, 0);
+            issue_sdp(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_sdp(j + 1);
+                mbar_wait(ds_full, (uint32_t)j & 1);
+                tc_fence_after();
+                const int itk = 2 * j;
+                mma_pv_128x128(tmem_base + 256, smem_u32(sdS), smem_u32(sRing + (itk & 3) * KV_BYTES), idesc_pv, j != 0);
+                umma_commit(&ring_empty[itk & 3]);
+                umma_commit(dq_done);
+            }
+        }
+    } else {
+        const int cw = warp - 2;
+        const int g = cw >> 2;       // column half of every S / dP row this warpgroup handles
+        const int quad = warp & 3;
+        const int r_in = quad * 32 + lane;
+        const int qi = q0 + r_in;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        {
+            const int nwords = n_key_tiles * 2;
+            for (int w = cw; w < nwords; w += 8) {
+                const int key = w * 32 + lane;
+                const bool ok = key < S && (!mask || mask[(long long)b * S + key] != 0);
+                const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) maskw[w] = bits;
+            }
+            compute_group_sync();
+        }
+        const bool row_ok = qi < S;
+        const float lse2 = row_ok ? lse[((long long)b * NH + h) * S + qi] * LOG2E : INFINITY;
+        const float dsum = row_ok ? Dsum[((long long)b * NH + h) * S + qi] : 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            const int sb = j & 1;
+            mbar_wait(&sdp_full[sb], (uint32_t)(j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32b_x32(lane_base + sb * BK + g * 32, sv);
+            tmem_ld_32x32b_x32(lane_base + 128 + sb * BK + g * 32, dv);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+
+            const int kbase = j * BK + g * 32;
+            const uint32_t mw = maskw[2 * j + g];
+            const bool plain = (kbase + 31 <= q0 + quad * 32) && mw == 0xffffffffu;  // warp-uniform
+            float ds[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const bool ok = plain || (kbase + c <= qi && ((mw >> c) & 1u));
+                const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2, -lse2)) : 0.f;
+                ds[c] = p * (__uint_as_float(dv[c]) - dsum);
+            }
+            if (j > 0) {
+                mbar_wait(dq_done, (uint32_t)(j - 1) & 1);  // dS buffer free again
+                tc_fence_after();
+            }
+            store_half_row(sdS, r_in, g, ds);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_full);
+        }
+        mbar_wait(dq_done, (uint32_t)(n_kv - 1) & 1);
+        tc_fence_after();
+        __nv_bfloat16* dqp = dqkv + ((long long)b * S + qi) * (3LL * NH * HD) + (long long)h * HD + g * 64;
+        store_acc_64(lane_base + 256 + g * 64, dqp, scale, row_ok);
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- dK, dV
+constexpr int KV_OFF_V = Q_BYTES;                 // K_j tile at 0, V_j tile at 32 KB (128 keys each)
+constexpr int KV_OFF_RING = 2 * Q_BYTES;          // Q_i / dO_i tiles of 64 queries
+constexpr int KV_OFF_PT = KV_OFF_RING + RING_SLOTS * KV_BYTES;
+constexpr int KV_OFF_DST = KV_OFF_PT + P_BYTES;
+constexpr int KV_OFF_BAR = KV_OFF_DST + P_BYTES;
+constexpr int KV_OFF_ROWV = KV_OFF_BAR + 256;     // float [2][2][64]: lse*log2e and D of the streamed queries
+constexpr int KV_SMEM_BYTES = KV_OFF_ROWV + 2 * 2 * 64 * 4 + 1024;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const unsigned char* __restrict__ mask, const float* __restrict__ lse,
+                        const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
+                        float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + KV_OFF_V;
+    uint8_t* sRing = smem + KV_OFF_RING;
+    uint8_t* sPT = smem + KV_OFF_PT;
+    uint8_t* sdST = smem + KV_OFF_DST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + KV_OFF_BAR);
+    uint64_t* kv_full = bars;                      // [1]
+    uint64_t* ring_full = bars + 1;                // [4]
+    uint64_t* ring_empty = ring_full + RING_SLOTS; // [4]
+    uint64_t* sdp_full = ring_empty + RING_SLOTS;  // [2]
+    uint64_t* sdp_empty = sdp_full + 2;            // [2]
+    uint64_t* pds_full = sdp_empty + 2;            // [1]  P^T and dS^T tiles written
+    uint64_t* pds_done = pds_full + 1;             // [1]  dV / dK MMAs of the tile retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pds_done + 1);
+    float* rowv = reinterpret_cast<float*>(smem + KV_OFF_ROWV);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x;  // key tile 0 has the most query tiles and starts first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int k0 = kt * BQ;
+    const int n_q_tiles = (S + BK - 1) / BK;
+    const int t0 = k0 / BK;               // first 64-query tile that can see these keys
+    const int n_it = n_q_tiles - t0;      // >= 1 because k0 < S
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < RING_SLOTS; ++i) {
+            mbar_init(&ring_full[i], 1);
+            mbar_init(&ring_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sdp_full[i], 1);
+            mbar_init(&sdp_empty[i], 8);
+        }
+        mbar_init(pds_full, 8);
+        mbar_init(pds_done, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;  // S^T[2] @ 0,64   dP^T[2] @ 128,192   dV @ 256   dK @ 384
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int row0 = b * S;
+            const int cq = h * HD, ck = NH * HD + h * HD, cv = 2 * NH * HD + h * HD;
+            mbar_arrive_expect_tx(kv_full, 2 * Q_BYTES);
+            for (int c = 0; c < 2; ++c)
+                for (int rh = 0; rh < 2; ++rh) {
+                    tma_load_2d(sK + c * (BQ * 128) + rh * (64 * 128), &tm_qkv, kv_full, ck + c * 64, row0 + k0 + rh * 64);
+                    tma_load_2d(sV + c * (BQ * 128) + rh * (64 * 128), &tm_qkv, kv_full, cv + c * 64, row0 + k0 + rh * 64);
+                }
+            for (int t = 0; t < n_it; ++t) {
+                const int qrow = row0 + (t0 + t) * BK;
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {  // 0: Q_t, 1: dO_t
+                    const int it = 2 * t + which, slot = it & 3;
+                    mbar_wait(&ring_empty[slot], (((uint32_t)it >> 2) & 1) ^ 1);
+                    uint8_t* dst = sRing + slot * KV_BYTES;
+                    mbar_arrive_expect_tx(&ring_full[slot], KV_BYTES);
+                    const CUtensorMap* tm = which ? &tm_do : &tm_qkv;
+                    tma_load_2d(dst, tm, &ring_full[slot], cq, qrow);
+                    tma_load_2d(dst + BK * 128, tm, &ring_full[slot], cq + 64, qrow);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_kk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BK >> 3) << 17) |
+                                      ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) |
+                                      ((uint32_t)(BQ >> 4) << 24);
+            auto issue_sdp = [&](int t) {
+                const int sb = t & 1;
+                const int itq = 2 * t, itd = 2 * t + 1;
+                mbar_wait(&sdp_empty[sb], ((uint32_t)(t >> 1) & 1) ^ 1);
+                mbar_wait(&ring_full[itq & 3], ((uint32_t)itq >> 2) & 1);
+                tc_fence_after();
+                mma_kk_128x64(tmem_base + sb * BK, smem_u32(sK), BQ * 128, smem_u32(sRing + (itq & 3) * KV_BYTES),
+                              BK * 128, idesc_kk);
+                mbar_wait(&ring_full[itd & 3], ((uint32_t)itd >> 2) & 1);
+                tc_fence_after();
+                mma_kk_128x64(tmem_base + 128 + sb * BK, smem_u32(sV), BQ * 128,
+                              smem_u32(sRing + (itd & 3) * KV_BYTES), BK * 128, idesc_kk);
+                umma_commit(&sdp_full[sb]);
+            };
+            mbar_wait(kv_full, 0);
+            issue_sdp(0);
+            for (int t = 0; t < n_it; ++t) {
+                if (t + 1 < n_it) issue_sdp(t + 1);
+                mbar_wait(pds_full, (uint32_t)t & 1);
+                tc_fence_after();
+                const int itq = 2 * t, itd = 2 * t + 1;
+                mma_pv_128x128(tmem_base + 256, smem_u32(sPT), smem_u32(sRing + (itd & 3) * KV_BYTES), idesc_pv, t != 0);
+                umma_commit(&ring_empty[itd & 3]);
+                mma_pv_128x128(tmem_base + 384, smem_u32(sdST), smem_u32(sRing + (itq & 3) * KV_BYTES), idesc_pv, t != 0);
+                umma_commit(&ring_empty[itq & 3]);
+                umma_commit(pds_done);
+            }
+        }
+    } else {
+        const int cw = warp - 2;
+        const int g = cw >> 2;
+        const int quad = warp & 3;
+        const int r_in = quad * 32 + lane;   // key row inside the tile == TMEM lane
+        const int key = k0 + r_in;
+        const int ct = threadIdx.x - 64;     // 0..255 inside the compute group
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const bool kvalid = key < S && (!mask || mask[(long long)b * S + key] != 0);
+        const float* lse_bh = lse + ((long long)b * NH + h) * S;
+        const float* d_bh = Dsum + ((long long)b * NH + h) * S;
+        for (int t = 0; t < n_it; ++t) {
+            const int sb = t & 1;
+            const int qb = (t0 + t) * BK;  // first query of the streamed tile
+            float* rv = rowv + sb * 128;
+            if (ct < 128) {
+                const int q = qb + (ct & 63);
+                float v;
+                if (ct < 64)
+                    v = q < S ? lse_bh[q] * LOG2E : INFINITY;  // +inf => p = 0 for queries past the sequence
+                else
+                    v = q < S ? d_bh[q] : 0.f;
+                rv[ct] = v;
+            }
+            compute_group_sync();  // also orders tile t-2's readers of this buffer before the writes above (see t-1)
+            mbar_wait(&sdp_full[sb], (uint32_t)(t >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32b_x32(lane_base + sb * BK + g * 32, sv);
+            tmem_ld_32x32b_x32(lane_base + 128 + sb * BK + g * 32, dv);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sdp_empty[sb]);
+
+            const int qc0 = qb + g * 32;  // query of column 0 of this half row
+            const bool plain = qc0 >= k0 + quad * 32 + 31;  // warp-uniform: every query of the half row sees every key
+            float pt[32], ds[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const bool ok = kvalid && (plain || qc0 + c >= key);
+                const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2, -rv[g * 32 + c])) : 0.f;
+                pt[c] = p;
+                ds[c] = p * (__uint_as_float(dv[c]) - rv[64 + g * 32 + c]);
+            }
+            if (t > 0) {
+                mbar_wait(pds_done, (uint32_t)(t - 1) & 1);
+                tc_fence_after();
+            }
+            store_half_row(sPT, r_in, g, pt);
+            store_half_row(sdST, r_in, g, ds);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+        }
+        mbar_wait(pds_done, (uint32_t)(n_it - 1) & 1);
+        tc_fence_after();
+        __nv_bfloat16* dkp = dqkv + ((long long)b * S + key) * (3LL * NH * HD) + (long long)NH * HD + (long long)h * HD +
+                             g * 64;
+        __nv_bfloat16* dvp = dkp + (long long)NH * HD;
+        store_acc_64(lane_base + 256 + g * 64, dvp, 1.f, key < S);
+        store_acc_64(lane_base + 384 + g * 64, dkp, scale, key < S);
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace atc
 
 // Returns LLARK_OK when the tcgen05 kernel was launched, LLARK_EINVAL when the shape is outside its envelope
@@ -373,6 +833,43 @@ int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out
     dim3 grid((S + BQ - 1) / BQ, n_heads, B);
     attn_fwd_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tm, key_mask, (__nv_bfloat16*)out, lse, S, n_heads,
                                                            scale * LOG2E);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return LLARK_ECUDA;
+    }
+    return LLARK_OK;
+}
+
+// Backward (dq|dk|dv into dqkv) on tcgen05; Dsum must already hold rowsum(dO o O). LLARK_EINVAL = shape outside the
+// envelope (caller falls back to the mma.sync kernels).
+int attn_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
+                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, cudaStream_t st) {
+    using namespace atc;
+    if ((long long)B * S > 0x7fffffffLL || S > MAX_S) return LLARK_EINVAL;
+    CUtensorMap tq, td;
+    const long long ld = 3LL * n_heads * HD, ldo = (long long)n_heads * HD;
+    int rc = tensor_map_2d(&tq, qkv, ld, (long long)B * S, ld, 64, 64, 2);
+    if (rc) return rc;
+    rc = tensor_map_2d(&td, dout, ldo, (long long)B * S, ldo, 64, 64, 2);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             DQ_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KV_SMEM_BYTES);
+        if (e != cudaSuccess) {
+            g_last_cuda_error = (int)e;
+            return LLARK_ECUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((S + BQ - 1) / BQ, n_heads, B);
+    attn_bwd_dkdv_tc_kernel<<<grid, kBwdThreads, KV_SMEM_BYTES, st>>>(tq, td, key_mask, lse, Dsum, (__nv_bfloat16*)dqkv,
+                                                                      S, n_heads, scale, scale * LOG2E);
+    attn_bwd_dq_tc_kernel<<<grid, kBwdThreads, DQ_SMEM_BYTES, st>>>(tq, td, key_mask, lse, Dsum, (__nv_bfloat16*)dqkv, S,
+                                                                    n_heads, scale, scale * LOG2E);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         g_last_cuda_error = (int)e;

@@ -27,6 +27,16 @@ for (b, h) in ((0, 0), (B - 1, NH - 1)):
 dout = torch.randn_like(out)
 ws = torch.empty(ops.lib().llark_attn_bwd_workspace(B, S, NH), device="cuda", dtype=torch.uint8)
 dqkv = torch.empty_like(qkv)
+# backward against fp32 autograd on one (batch, head)
+ops.attn_bwd(qkv, None, out, dout, lse, B, S, NH, D, dqkv=dqkv, workspace=ws)
+b, h = B - 1, 1
+x = qkv.view(B, S, 3, NH, D)[b, :, :, h].float().clone().requires_grad_(True)
+sc = (x[:, 0] @ x[:, 1].t()) / D ** 0.5
+sc = sc.masked_fill(torch.triu(torch.ones(S, S, device="cuda", dtype=torch.bool), 1), float("-inf"))
+(torch.softmax(sc, -1) @ x[:, 2]).backward(dout.view(B, S, NH, D)[b, :, h].float())
+gref = x.grad  # [S, 3, D]
+ggot = dqkv.view(B, S, 3, NH, D)[b, :, :, h].float()
+err_b = [((ggot[:, i] - gref[:, i]).norm() / gref[:, i].norm()).item() for i in range(3)]
 
 def t(fn, n=20):
     for _ in range(3):
@@ -45,4 +55,4 @@ us_b = t(lambda: ops.attn_bwd(qkv, None, out, dout, lse, B, S, NH, D, dqkv=dqkv,
 fl = 4.0 * S * S * D * NH * B / 2
 print(json.dumps({"attn_tc": os.environ.get("LLARK_ATTN_TC", "1"), "B": B, "S": S, "fwd_us": round(us_f, 1),
                   "bwd_us": round(us_b, 1), "fwd_tflops_causal": round(fl / us_f / 1e6, 1),
-                  "bwd_tflops_causal": round(2.5 * fl / us_b / 1e6, 1), "fwd_rel_err": err, "lse_abs_err": err_l}))
+                  "bwd_tflops_causal": round(2.5 * fl / us_b / 1e6, 1), "fwd_rel_err": err, "lse_abs_err": err_l, "bwd_rel_err_qkv": err_b}))
