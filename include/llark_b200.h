@@ -43,6 +43,26 @@ int llark_last_cuda_error(void);
 int llark_gemm(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, void* C,
                long long ldc, int c_fp32, const void* bias, int bias_fp32, const void* R, long long ldr, int M, int N,
                int K, int in_fp32, int max_ctas, cudaStream_t stream);
+/* Fused epilogues of the GEMM core (llark_gemm_ex; ep == NULL or kind 0 behaves exactly like llark_gemm):
+ *   LLARK_EPI_QUICK_GELU  C = quick_gelu(acc + bias)            -- prior MLP `fc` (openai/jukebox MLP, reached from
+ *                                                                  jukebox/main.py:108); replaces llark_quick_gelu (+ cast)
+ *   LLARK_EPI_ROPE        columns [0, i1) of C (q | k heads of the fused QKV projection, head_dim 128) are rotated
+ *                         with a = cos, b = sin (bf16 [S,128]), position = row % i0 -- transformers
+ *                         apply_rotary_pos_emb reached from m2t/models/llamav2.py:224; replaces llark_rope(inverse=0)
+ *   LLARK_EPI_SWIGLU_BWD  acc = d(act) of the down projection's dgrad; a = gu bf16 [M, ld] (gate | up, N apart);
+ *                         C[:, c] = dgate, C[:, N + c] = dup (C is dgu [M, ldc >= 2N]); replaces llark_swiglu_bwd
+ * Results are bit-identical to the unfused sequences (same bf16 rounding points). */
+enum { LLARK_EPI_NONE = 0, LLARK_EPI_QUICK_GELU = 1, LLARK_EPI_ROPE = 2, LLARK_EPI_SWIGLU_BWD = 3 };
+typedef struct LlarkGemmEpilogue {
+    int kind;
+    const void* a;
+    const void* b;
+    long long ld;
+    int i0, i1;
+} LlarkGemmEpilogue;
+int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, void* C,
+                  long long ldc, int c_fp32, const void* bias, int bias_fp32, const void* R, long long ldr, int M, int N,
+                  int K, int in_fp32, int max_ctas, const LlarkGemmEpilogue* ep, cudaStream_t stream);
 void llark_gemm_clear_cache(void);
 /* Kernel variant: 1 = CTA-pair kernel (cta_group::2, 256x256 tile per 2-CTA cluster; default), 0 = single-CTA
  * kernel (128x256 tile). Default comes from the environment variable LLARK_GEMM_2CTA (unset or != "0" -> 1). */
@@ -167,6 +187,11 @@ int llark_jb_embed_tokens(const long long* codes, const float* emb, const float*
  * nothing -> zeros). out fp32 [N*T, heads*dh]. */
 int llark_jb_sparse_attn(const float* qkv, float* out, int N, int T, int heads, int dh, int block, int pattern,
                          cudaStream_t stream);
+/* Same contract on tensor cores (mma.sync m16n8k8: operands rounded to TF32, fp32 accumulate and softmax): groups of
+ * 64 or 128 rows, even dh <= 152. out: fp32, or bf16 when out_bf16 != 0 (the bf16 prior's cast fused in). Returns
+ * LLARK_EINVAL for a geometry outside that envelope (use llark_jb_sparse_attn then). */
+int llark_jb_sparse_attn_tc(const float* qkv, void* out, int out_bf16, int N, int T, int heads, int dh, int block,
+                            int pattern, cudaStream_t stream);
 /* y = x * sigmoid(1.702 x) in place-safe form. */
 int llark_quick_gelu(const float* x, float* y, long long n, cudaStream_t stream);
 /* out = a + b + c (c may be NULL). */

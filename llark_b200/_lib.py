@@ -7,23 +7,34 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllark_b200.so")
+# LLARK_LIB_PATH: A/B perf experiments against another build of the same C-ABI (tools/); never a fallback
+LIB_PATH = os.environ.get("LLARK_LIB_PATH") or os.path.join(_HERE, "libllark_b200.so")
 
 _ERR = {-1: "LLARK_EINVAL (bad shape/alignment/argument)", -2: "LLARK_ECUDA", -3: "LLARK_EDRIVER", -4: "LLARK_ENCCL"}
 
 # every symbol include/llark_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "llark_last_cuda_error", "llark_gemm", "llark_gemm_clear_cache", "llark_gemm_set_mode", "llark_gemm_get_mode", "llark_splice_scan", "llark_embed_splice_fwd",
+    "llark_last_cuda_error", "llark_gemm", "llark_gemm_ex", "llark_gemm_clear_cache", "llark_gemm_set_mode", "llark_gemm_get_mode", "llark_splice_scan", "llark_embed_splice_fwd",
     "llark_embed_splice_bwd", "llark_cast_f32_to_bf16", "llark_cast_bf16_to_f32", "llark_rmsnorm_fwd",
     "llark_rmsnorm_bwd_workspace", "llark_rmsnorm_bwd", "llark_rope", "llark_swiglu_fwd", "llark_swiglu_bwd",
     "llark_attn_fwd", "llark_attn_bwd_workspace", "llark_attn_bwd", "llark_ce_fwd", "llark_ce_bwd",
     "llark_sumsq_workspace", "llark_grad_sumsq", "llark_adamw_step", "llark_comm_unique_id", "llark_comm_init",
     "llark_comm_destroy", "llark_grad_bucket_allreduce", "llark_jb_conv_down", "llark_jb_resblock",
     "llark_jb_conv_k3", "llark_jb_vq_encode", "llark_layernorm_fwd", "llark_jb_embed_tokens", "llark_jb_sparse_attn",
+    "llark_jb_sparse_attn_tc",
     "llark_quick_gelu", "llark_add3", "llark_jb_pool", "llark_colsum",
 ]
 
 _lib = None
+
+
+class GemmEpilogue(ctypes.Structure):
+    """LlarkGemmEpilogue of include/llark_b200.h."""
+    _fields_ = [("kind", ctypes.c_int), ("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("ld", ctypes.c_longlong),
+                ("i0", ctypes.c_int), ("i1", ctypes.c_int)]
+
+
+EPI_NONE, EPI_QUICK_GELU, EPI_ROPE, EPI_SWIGLU_BWD = 0, 1, 2, 3
 
 
 class LlarkError(RuntimeError):
@@ -47,6 +58,7 @@ def lib():
         sig = {
             "llark_last_cuda_error": ([], I),
             "llark_gemm": ([P, I, LL, P, I, LL, P, LL, I, P, I, P, LL, I, I, I, I, I, P], I),
+            "llark_gemm_ex": ([P, I, LL, P, I, LL, P, LL, I, P, I, P, LL, I, I, I, I, I, P, P], I),
             "llark_gemm_clear_cache": ([], None),
             "llark_gemm_set_mode": ([I], None),
             "llark_gemm_get_mode": ([], I),
@@ -80,12 +92,15 @@ def lib():
             "llark_layernorm_fwd": ([P, P, P, P, I, LL, I, F, P], I),
             "llark_jb_embed_tokens": ([P, P, P, P, P, P, I, I, I, P], I),
             "llark_jb_sparse_attn": ([P, P, I, I, I, I, I, I, P], I),
+            "llark_jb_sparse_attn_tc": ([P, P, I, I, I, I, I, I, I, P], I),
             "llark_quick_gelu": ([P, P, LL, P], I),
             "llark_add3": ([P, P, P, P, LL, P], I),
             "llark_jb_pool": ([P, P, I, I, I, P], I),
             "llark_colsum": ([P, P, LL, I, I, P], I),
         }
         for name, (argtypes, restype) in sig.items():
+            if os.environ.get("LLARK_LIB_PATH") and not hasattr(_lib, name):
+                continue  # A/B run against an older build of the C-ABI: newer entry points are simply absent
             fn = getattr(_lib, name)
             fn.argtypes = argtypes
             fn.restype = restype

@@ -427,7 +427,7 @@ __device__ __forceinline__ void store_acc_64(uint32_t taddr, __nv_bfloat16* dst,
 constexpr int DQ_OFF_DO = Q_BYTES;
 constexpr int DQ_OFF_RING = 2 * Q_BYTES;
 constexpr int DQ_OFF_DS = DQ_OFF_RING + RING_SLOTS * KV_BYTES;
-constexpr int DQ_OFF_BAR = DQ_OFF_DS + P_BYTES;
+constexpr int DQ_OFF_BAR = DQ_OFF_DS + 2 * P_BYTES;  // dS is double-buffered
 constexpr int DQ_OFF_MASK = DQ_OFF_BAR + 256;
 constexpr int DQ_SMEM_BYTES = DQ_OFF_MASK + (MAX_S / 32) * 4 + 1024;
 
@@ -448,9 +448,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     uint64_t* ring_empty = ring_full + RING_SLOTS; // [4]
     uint64_t* sdp_full = ring_empty + RING_SLOTS;  // [2]  S and dP of tile j are in TMEM
     uint64_t* sdp_empty = sdp_full + 2;            // [2]  8 compute warps have read them
-    uint64_t* ds_full = sdp_empty + 2;             // [1]  dS tile written to shared memory
-    uint64_t* dq_done = ds_full + 1;               // [1]  dQ += dS K_j retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 1);
+    uint64_t* ds_full = sdp_empty + 2;             // [2]  dS tile j written to shared-memory buffer j & 1
+    uint64_t* dq_done = ds_full + 2;               // [2]  dQ += dS_j K_j retired (buffer j & 1 free again)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 2);
     uint32_t* maskw = reinterpret_cast<uint32_t*>(smem + DQ_OFF_MASK);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -472,8 +472,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             mbar_init(&sdp_full[i], 1);
             mbar_init(&sdp_empty[i], 8);
         }
-        mbar_init(ds_full, 8);
-        mbar_init(dq_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&ds_full[i], 8);
+            mbar_init(&dq_done[i], 1);
+        }
         mbar_fence_init();
         fence_proxy_async_smem();
     }
@@ -534,12 +536,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             issue_sdp(0);
             for (int j = 0; j < n_kv; ++j) {
                 if (j + 1 < n_kv) issue_sdp(j + 1);
-                mbar_wait(ds_full, (uint32_t)j & 1);
+                mbar_wait(&ds_full[j & 1], (uint32_t)(j >> 1) & 1);
                 tc_fence_after();
                 const int itk = 2 * j;
-                mma_pv_128x128(tmem_base + 256, smem_u32(sdS), smem_u32(sRing + (itk & 3) * KV_BYTES), idesc_pv, j != 0);
+                mma_pv_128x128(tmem_base + 256, smem_u32(sdS + (j & 1) * P_BYTES),
+                               smem_u32(sRing + (itk & 3) * KV_BYTES), idesc_pv, j != 0);
                 umma_commit(&ring_empty[itk & 3]);
-                umma_commit(dq_done);
+                umma_commit(&dq_done[j & 1]);
             }
         }
     } else {
@@ -584,17 +587,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2, -lse2)) : 0.f;
                 ds[c] = p * (__uint_as_float(dv[c]) - dsum);
             }
-            if (j > 0) {
-                mbar_wait(dq_done, (uint32_t)(j - 1) & 1);  // dS buffer free again
+            if (j >= 2) {
+                mbar_wait(&dq_done[j & 1], (uint32_t)((j >> 1) - 1) & 1);  // tile j-2 retired: buffer j & 1 is free
                 tc_fence_after();
             }
-            store_half_row(sdS, r_in, g, ds);
+            store_half_row(sdS + (j & 1) * P_BYTES, r_in, g, ds);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(ds_full);
+            if (lane == 0) mbar_arrive(&ds_full[j & 1]);
         }
-        mbar_wait(dq_done, (uint32_t)(n_kv - 1) & 1);
+        mbar_wait(&dq_done[(n_kv - 1) & 1], (uint32_t)((n_kv - 1) >> 1) & 1);  // MMAs retire in order
         tc_fence_after();
         __nv_bfloat16* dqp = dqkv + ((long long)b * S + qi) * (3LL * NH * HD) + (long long)h * HD + g * 64;
         store_acc_64(lane_base + 256 + g * 64, dqp, scale, row_ok);
@@ -614,8 +617,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 constexpr int KV_OFF_V = Q_BYTES;                 // K_j tile at 0, V_j tile at 32 KB (128 keys each)
 constexpr int KV_OFF_RING = 2 * Q_BYTES;          // Q_i / dO_i tiles of 64 queries
 constexpr int KV_OFF_PT = KV_OFF_RING + RING_SLOTS * KV_BYTES;
-constexpr int KV_OFF_DST = KV_OFF_PT + P_BYTES;
-constexpr int KV_OFF_BAR = KV_OFF_DST + P_BYTES;
+constexpr int KV_OFF_DST = KV_OFF_PT + 2 * P_BYTES;   // P^T and dS^T are double-buffered
+constexpr int KV_OFF_BAR = KV_OFF_DST + 2 * P_BYTES;
 constexpr int KV_OFF_ROWV = KV_OFF_BAR + 256;     // float [2][2][64]: lse*log2e and D of the streamed queries
 constexpr int KV_SMEM_BYTES = KV_OFF_ROWV + 2 * 2 * 64 * 4 + 1024;
 
@@ -637,9 +640,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint64_t* ring_empty = ring_full + RING_SLOTS; // [4]
     uint64_t* sdp_full = ring_empty + RING_SLOTS;  // [2]
     uint64_t* sdp_empty = sdp_full + 2;            // [2]
-    uint64_t* pds_full = sdp_empty + 2;            // [1]  P^T and dS^T tiles written
-    uint64_t* pds_done = pds_full + 1;             // [1]  dV / dK MMAs of the tile retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pds_done + 1);
+    uint64_t* pds_full = sdp_empty + 2;            // [2]  P^T and dS^T of tile t written to buffers t & 1
+    uint64_t* pds_done = pds_full + 2;             // [2]  dV / dK MMAs of tile t retired (buffers t & 1 free)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pds_done + 2);
     float* rowv = reinterpret_cast<float*>(smem + KV_OFF_ROWV);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -662,8 +665,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             mbar_init(&sdp_full[i], 1);
             mbar_init(&sdp_empty[i], 8);
         }
-        mbar_init(pds_full, 8);
-        mbar_init(pds_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&pds_full[i], 8);
+            mbar_init(&pds_done[i], 1);
+        }
         mbar_fence_init();
         fence_proxy_async_smem();
     }
@@ -724,14 +729,16 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             issue_sdp(0);
             for (int t = 0; t < n_it; ++t) {
                 if (t + 1 < n_it) issue_sdp(t + 1);
-                mbar_wait(pds_full, (uint32_t)t & 1);
+                mbar_wait(&pds_full[t & 1], (uint32_t)(t >> 1) & 1);
                 tc_fence_after();
                 const int itq = 2 * t, itd = 2 * t + 1;
-                mma_pv_128x128(tmem_base + 256, smem_u32(sPT), smem_u32(sRing + (itd & 3) * KV_BYTES), idesc_pv, t != 0);
+                mma_pv_128x128(tmem_base + 256, smem_u32(sPT + (t & 1) * P_BYTES),
+                               smem_u32(sRing + (itd & 3) * KV_BYTES), idesc_pv, t != 0);
                 umma_commit(&ring_empty[itd & 3]);
-                mma_pv_128x128(tmem_base + 384, smem_u32(sdST), smem_u32(sRing + (itq & 3) * KV_BYTES), idesc_pv, t != 0);
+                mma_pv_128x128(tmem_base + 384, smem_u32(sdST + (t & 1) * P_BYTES),
+                               smem_u32(sRing + (itq & 3) * KV_BYTES), idesc_pv, t != 0);
                 umma_commit(&ring_empty[itq & 3]);
-                umma_commit(pds_done);
+                umma_commit(&pds_done[t & 1]);
             }
         }
     } else {
@@ -745,19 +752,21 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const bool kvalid = key < S && (!mask || mask[(long long)b * S + key] != 0);
         const float* lse_bh = lse + ((long long)b * NH + h) * S;
         const float* d_bh = Dsum + ((long long)b * NH + h) * S;
+        // lse*log2e (threads 0-63) / D (threads 64-127) of the streamed queries, fetched one tile ahead so the global
+        // load latency is off the per-tile critical path
+        auto fetch_rowv = [&](int t) -> float {
+            if (ct >= 128 || t >= n_it) return 0.f;
+            const int q = (t0 + t) * BK + (ct & 63);
+            if (ct < 64) return q < S ? lse_bh[q] * LOG2E : INFINITY;  // +inf => p = 0 past the sequence end
+            return q < S ? d_bh[q] : 0.f;
+        };
+        float rowv_next = fetch_rowv(0);
         for (int t = 0; t < n_it; ++t) {
             const int sb = t & 1;
             const int qb = (t0 + t) * BK;  // first query of the streamed tile
             float* rv = rowv + sb * 128;
-            if (ct < 128) {
-                const int q = qb + (ct & 63);
-                float v;
-                if (ct < 64)
-                    v = q < S ? lse_bh[q] * LOG2E : INFINITY;  // +inf => p = 0 for queries past the sequence
-                else
-                    v = q < S ? d_bh[q] : 0.f;
-                rv[ct] = v;
-            }
+            if (ct < 128) rv[ct] = rowv_next;
+            rowv_next = fetch_rowv(t + 1);
             compute_group_sync();  // also orders tile t-2's readers of this buffer before the writes above (see t-1)
             mbar_wait(&sdp_full[sb], (uint32_t)(t >> 1) & 1);
             tc_fence_after();
@@ -779,18 +788,18 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 pt[c] = p;
                 ds[c] = p * (__uint_as_float(dv[c]) - rv[64 + g * 32 + c]);
             }
-            if (t > 0) {
-                mbar_wait(pds_done, (uint32_t)(t - 1) & 1);
+            if (t >= 2) {
+                mbar_wait(&pds_done[t & 1], (uint32_t)((t >> 1) - 1) & 1);  // tile t-2 retired: buffers t & 1 free
                 tc_fence_after();
             }
-            store_half_row(sPT, r_in, g, pt);
-            store_half_row(sdST, r_in, g, ds);
+            store_half_row(sPT + (t & 1) * P_BYTES, r_in, g, pt);
+            store_half_row(sdST + (t & 1) * P_BYTES, r_in, g, ds);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(pds_full);
+            if (lane == 0) mbar_arrive(&pds_full[t & 1]);
         }
-        mbar_wait(pds_done, (uint32_t)(n_it - 1) & 1);
+        mbar_wait(&pds_done[(n_it - 1) & 1], (uint32_t)((n_it - 1) >> 1) & 1);  // MMAs retire in order
         tc_fence_after();
         __nv_bfloat16* dkp = dqkv + ((long long)b * S + key) * (3LL * NH * HD) + (long long)NH * HD + (long long)h * HD +
                              g * 64;

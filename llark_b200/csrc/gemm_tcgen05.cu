@@ -51,7 +51,29 @@ struct GemmParams {
     int* tile_counter;   // CTA-pair kernel: dynamic tile scheduler counter (zero at launch, reset by the last fetch)
     int debug;       // LLARK_GEMM_DEBUG bits (perf experiments only): 1 = split K-major boxes in 64-row halves,
                      // 2 = producer issues no TMA (MMA runs on stale smem: isolates the UMMA rate)
+    // fused epilogue (LlarkGemmEpilogue): 0 none, 1 quick-GELU, 2 RoPE on the first epi_i1 columns (head_dim 128,
+    // position = row % epi_i0, epi_a / epi_b = cos / sin bf16 [S,128]), 3 SwiGLU backward (epi_a = gu bf16 [M, epi_ld]:
+    // gate | up halves N apart; C receives dgate at column c and dup at column N + c)
+    int epi;
+    const void* epi_a;
+    const void* epi_b;
+    long long epi_ld;
+    int epi_i0, epi_i1;
 };
+
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* ptr, float (&f)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(ptr);
+    const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* ptr, const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(ptr) = o;
+}
 
 // SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B).
@@ -84,6 +106,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int 
 }
 
 // One 32-column chunk of one accumulator row: bias / residual, conversion, 16-byte stores (N tail masked).
+template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, long long row, int col0,
                                      const uint32_t (&v)[32]) {
 #pragma unroll
@@ -101,6 +124,30 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, long l
                     f[e] += p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[col + e]
                                         : __bfloat162float(
                                               reinterpret_cast<const __nv_bfloat16*>(p.bias)[col + e]);
+        }
+        if constexpr (EPI == 1) {
+            // quick-GELU of the prior MLP (x * sigmoid(1.702 x)), same formula as llark_quick_gelu
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = f[e] / (1.f + __expf(-1.702f * f[e]));
+        } else if constexpr (EPI == 3) {
+            // SwiGLU backward fused into the down-projection dgrad: the accumulator is d(act) (rounded to bf16 as
+            // the unfused GEMM would store it); same arithmetic as swiglu_bwd_kernel (llama_ops.cu)
+            const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(p.epi_a) + row * p.epi_ld + col;
+            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
+            float g[8], u[8], dg[8], du[8];
+            ld8_bf16(gptr, g);
+            ld8_bf16(gptr + p.N, u);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = bf16_round(f[e]);
+                const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
+                const float silu = g[e] * sg;
+                du[e] = d * bf16_round(silu);
+                dg[e] = d * u[e] * (sg * (1.f + g[e] * (1.f - sg)));
+            }
+            st8_bf16(cptr, dg);
+            st8_bf16(cptr + p.N, du);
+            continue;
         }
         if (p.c_fp32) {
             float* cptr = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
@@ -153,7 +200,61 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, long l
     }
 }
 
-template <int A_MN, int B_MN, int TF32>
+// All 256 accumulator columns of one row (this thread's TMEM lane): 8 chunks of 32 columns through
+// epilogue_store_chunk, or -- for the q and k columns of a fused-RoPE QKV projection -- pairs of chunks 64 columns
+// apart rotated as HF apply_rotary_pos_emb does in bf16: x = bf16(acc) (the Linear output),
+// out = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), identical to llark_rope applied after an unfused GEMM.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, long long row, bool row_ok, int ncol0,
+                                              uint32_t taddr) {
+    if (EPI == 2 && ncol0 < p.epi_i1) {
+        const int spos = (int)(row % p.epi_i0);
+        const __nv_bfloat16* cs = reinterpret_cast<const __nv_bfloat16*>(p.epi_a) + (long long)spos * 128;
+        const __nv_bfloat16* sn = reinterpret_cast<const __nv_bfloat16*>(p.epi_b) + (long long)spos * 128;
+#pragma unroll 1
+        for (int hc = 0; hc < 4; ++hc) {
+            const int clo = (hc >> 1) * 128 + (hc & 1) * 32;  // tile-local column of the low-half chunk
+            if (ncol0 + clo >= p.N) break;                    // warp-uniform (N % 128 == 0 is checked on the host)
+            uint32_t lo[32], hi[32];
+            tmem_ld_32x32b_x32(taddr + clo, lo);
+            tmem_ld_32x32b_x32(taddr + clo + 64, hi);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + ncol0 + clo;
+            const int i0 = (hc & 1) * 32;  // index inside the half head
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float c1[8], s1[8], c2[8], s2[8], o1[8], o2[8];
+                ld8_bf16(cs + i0 + j * 8, c1);
+                ld8_bf16(sn + i0 + j * 8, s1);
+                ld8_bf16(cs + 64 + i0 + j * 8, c2);
+                ld8_bf16(sn + 64 + i0 + j * 8, s2);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float x1 = bf16_round(__uint_as_float(lo[j * 8 + e]));
+                    const float x2 = bf16_round(__uint_as_float(hi[j * 8 + e]));
+                    o1[e] = bf16_round(x1 * c1[e]) + bf16_round(-x2 * s1[e]);
+                    o2[e] = bf16_round(x2 * c2[e]) + bf16_round(x1 * s2[e]);
+                }
+                st8_bf16(cptr + j * 8, o1);
+                st8_bf16(cptr + 64 + j * 8, o2);
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = ncol0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        epilogue_store_chunk<EPI>(p, row, col0, v);
+    }
+}
+
+template <int A_MN, int B_MN, int TF32, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmParams p) {
@@ -292,16 +393,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tc_fence_after();
             const long long row = (long long)tc.m_blk * BLOCK_M + ew * 32 + lane;
             const bool row_ok = row < p.M;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                const int col0 = tc.n_blk * BLOCK_N + c * 32;
-                if (col0 >= p.N) break;  // warp-uniform
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * 32, v);
-                tmem_ld_wait();
-                if (!row_ok) continue;
-                epilogue_store_chunk(p, row, col0, v);
-            }
+            epilogue_tile<EPI>(p, row, row_ok, tc.n_blk * BLOCK_N, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -328,10 +420,12 @@ constexpr int B2_STAGE_BYTES = 128 * BLOCK_KB;  // this CTA's half of B: 16 KB
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;  // 32 KB per CTA per stage
 constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 512;
 
-template <int A_MN, int B_MN, int TF32>
+template <int A_MN, int B_MN, int TF32, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const GemmParams p) {
+    constexpr int kElemBytes = TF32 ? 4 : 2;  // operand element size is a property of the instantiation
+
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * STAGE2_BYTES);
@@ -351,7 +445,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     const int cluster_id = blockIdx.x >> 1;
     // p.num_m_blocks counts 256-row blocks here
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-    const int elems_per_row = BLOCK_KB / p.elem_bytes;
+    const int elems_per_row = BLOCK_KB / kElemBytes;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -436,59 +530,62 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     if ((warp == 0 || (warp == 3 && split_prod)) && lane == 0) {
         // ===================== TMA producers (both CTAs) =====================
         const bool do_a = warp == 0, do_b = split_prod ? (warp == 3) : true;
+        // Everything that does not change per stage is computed out here: TMA issue from these two threads paces the
+        // MN-major kinds (profiles/r1_gemm_mn_major_investigation.md), and a build whose stage loop carried two integer
+        // divisions and a mapa lost 11 % on dgrad / wgrad (1403 -> 1248 TFLOP/s, same box, profiles/r1_session2_summary.md).
+        const int mn_per_box = 128 / kElemBytes;
+        const int box_bytes = elems_per_row * 128;
+        const uint32_t bar0 = mapa_shared(smem_u32(&full_bar[0]), 0);  // the leader's full barriers
+        const bool arm = leader && do_a;                               // this thread posts the expected byte count
+        const int a_mode = A_MN ? (p.a_tma4 == 2 ? 3 : (p.a_tma4 ? 4 : 2)) : ((p.debug & 1) ? 1 : 0);
+        const int b_mode = B_MN ? (p.b_tma4 == 2 ? 3 : (p.b_tma4 ? 4 : 2)) : ((p.debug & 1) ? 1 : 0);
+        const bool no_tma = (p.debug & 2) != 0;
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = next_tile(false); tile >= 0; tile = next_tile(false)) {
             const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
             const int m0 = tc.m_blk * 256 + (int)rank * 128;
             const int n0 = tc.n_blk * BLOCK_N + (int)rank * 128;
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            const int m_chunk = m0 / mn_per_box, n_chunk = n0 / mn_per_box;  // once per tile, not per stage
+            int k0 = 0;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb, k0 += elems_per_row) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * STAGE2_BYTES;
                 uint8_t* sb = sa + A_STAGE_BYTES;
-                const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
-                if (p.debug & 2) {
-                    if (leader && do_a) mbar_arrive(&full_bar[stage]);
-                    if (++stage == kStages2) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                    continue;
-                }
-                if (leader && do_a) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
-                const int k0 = kb * elems_per_row;
-                const int mn_per_box = 128 / p.elem_bytes;
-                const int box_bytes = elems_per_row * 128;
-                if (do_a) {
-                    if (A_MN == 0) {
-                        if (p.debug & 1) {
+                const uint32_t bar = bar0 + (uint32_t)stage * 8u;
+                if (no_tma) {
+                    if (arm) mbar_arrive(&full_bar[stage]);
+                } else {
+                    if (arm) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+                    if (do_a) {
+                        if (a_mode == 0) {
+                            tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
+                        } else if (a_mode == 3) {
+                            tma_load_3d_2sm(sa, &tma_a, bar, 0, k0, m_chunk);
+                        } else if (a_mode == 4) {
+                            tma_load_4d_2sm(sa, &tma_a, bar, 0, 0, m_chunk, k0 >> 3);
+                        } else if (a_mode == 1) {
                             tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
                             tma_load_2d_2sm(sa + 64 * 128, &tma_a, bar, k0, m0 + 64);
-                        } else
-                            tma_load_2d_2sm(sa, &tma_a, bar, k0, m0);
-                    } else if (p.a_tma4 == 2) {
-                        tma_load_3d_2sm(sa, &tma_a, bar, 0, k0, m0 / mn_per_box);
-                    } else if (p.a_tma4) {
-                        tma_load_4d_2sm(sa, &tma_a, bar, 0, 0, m0 / mn_per_box, k0 / 8);
-                    } else {
-                        for (int j = 0; j < 128 / mn_per_box; ++j)
-                            tma_load_2d_2sm(sa + j * box_bytes, &tma_a, bar, m0 + j * mn_per_box, k0);
+                        } else {
+                            for (int j = 0; j < 128 / mn_per_box; ++j)
+                                tma_load_2d_2sm(sa + j * box_bytes, &tma_a, bar, m0 + j * mn_per_box, k0);
+                        }
                     }
-                }
-                if (do_b) {
-                    if (B_MN == 0) {
-                        if (p.debug & 1) {
+                    if (do_b) {
+                        if (b_mode == 0) {
+                            tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
+                        } else if (b_mode == 3) {
+                            tma_load_3d_2sm(sb, &tma_b, bar, 0, k0, n_chunk);
+                        } else if (b_mode == 4) {
+                            tma_load_4d_2sm(sb, &tma_b, bar, 0, 0, n_chunk, k0 >> 3);
+                        } else if (b_mode == 1) {
                             tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
                             tma_load_2d_2sm(sb + 64 * 128, &tma_b, bar, k0, n0 + 64);
-                        } else
-                            tma_load_2d_2sm(sb, &tma_b, bar, k0, n0);
-                    } else if (p.b_tma4 == 2) {
-                        tma_load_3d_2sm(sb, &tma_b, bar, 0, k0, n0 / mn_per_box);
-                    } else if (p.b_tma4) {
-                        tma_load_4d_2sm(sb, &tma_b, bar, 0, 0, n0 / mn_per_box, k0 / 8);
-                    } else {
-                        for (int j = 0; j < 128 / mn_per_box; ++j)
-                            tma_load_2d_2sm(sb + j * box_bytes, &tma_b, bar, n0 + j * mn_per_box, k0);
+                        } else {
+                            for (int j = 0; j < 128 / mn_per_box; ++j)
+                                tma_load_2d_2sm(sb + j * box_bytes, &tma_b, bar, n0 + j * mn_per_box, k0);
+                        }
                     }
                 }
                 if (++stage == kStages2) {
@@ -509,7 +606,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const uint32_t mn_box_bytes = elems_per_row * 128;
         // MN-major smem layouts. 2-D path: [chunk][K rows][128 B]   -> LBO = box bytes, SBO = 1024, K-step = rows*128
         //                        4-D path: [K group][chunk][8][128 B] -> LBO = 1024, SBO = chunks*1024 (2 chunks = 128 MN)
-        const uint32_t k_rows_per_mma = 32 / p.elem_bytes;
+        const uint32_t k_rows_per_mma = 32 / kElemBytes;
         const bool a4 = p.a_tma4 == 1, b4 = p.b_tma4 == 1;  // (== 2: 3-D box, same smem layout as the 2-D path)
         const uint32_t a_lbo = amn ? (a4 ? 1024u : mn_box_bytes) : 0u;
         const uint32_t b_lbo = bmn ? (b4 ? 1024u : mn_box_bytes) : 0u;
@@ -563,16 +660,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             tc_fence_after();
             const long long row = (long long)tc.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane;
             const bool row_ok = row < p.M;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                const int col0 = tc.n_blk * BLOCK_N + c * 32;
-                if (col0 >= p.N) break;
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * 32, v);
-                tmem_ld_wait();
-                if (!row_ok) continue;
-                epilogue_store_chunk(p, row, col0, v);
-            }
+            epilogue_tile<EPI>(p, row, row_ok, tc.n_blk * BLOCK_N, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_empty0 + (uint32_t)as * 8u);
@@ -743,10 +831,10 @@ static int get_tensor_map_mn3(CUtensorMap* out, const void* ptr, long long mn, l
     return LLARK_OK;
 }
 
-template <int A_MN, int B_MN, int TF32>
+template <int A_MN, int B_MN, int TF32, int EPI = 0>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas, cudaStream_t stream) {
     static bool attr_set = false;
-    auto kfn = gemm_kernel<A_MN, B_MN, TF32>;
+    auto kfn = gemm_kernel<A_MN, B_MN, TF32, EPI>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {
@@ -767,10 +855,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     return LLARK_OK;
 }
 
-template <int A_MN, int B_MN, int TF32>
+template <int A_MN, int B_MN, int TF32, int EPI = 0>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas, cudaStream_t stream) {
     static bool attr_set = false;
-    auto kfn = gemm2_kernel<A_MN, B_MN, TF32>;
+    auto kfn = gemm2_kernel<A_MN, B_MN, TF32, EPI>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
         if (e != cudaSuccess) {
@@ -825,7 +913,36 @@ extern "C" int llark_gemm_get_mode(void) {
 extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
                           void* C, long long ldc, int c_fp32, const void* bias, int bias_fp32, const void* R,
                           long long ldr, int M, int N, int K, int in_fp32, int max_ctas, cudaStream_t stream) {
+    return llark_gemm_ex(A, a_mn_major, lda, B, b_mn_major, ldb, C, ldc, c_fp32, bias, bias_fp32, R, ldr, M, N, K,
+                         in_fp32, max_ctas, nullptr, stream);
+}
+
+extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                             long long ldb, void* C, long long ldc, int c_fp32, const void* bias, int bias_fp32,
+                             const void* R, long long ldr, int M, int N, int K, int in_fp32, int max_ctas,
+                             const LlarkGemmEpilogue* ep, cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) return LLARK_EINVAL;
+    if (ep && ep->kind != LLARK_EPI_NONE) {
+        switch (ep->kind) {
+            case LLARK_EPI_QUICK_GELU:
+                if (R) return LLARK_EINVAL;
+                break;
+            case LLARK_EPI_ROPE:
+                // bf16 output, no bias / residual, whole heads per tile half, rotated region ends on a tile boundary
+                if (c_fp32 || bias || R || !ep->a || !ep->b || ep->i0 <= 0 || (N % 128) || (ep->i1 % BLOCK_N) ||
+                    ep->i1 > N || ((reinterpret_cast<uintptr_t>(ep->a) | reinterpret_cast<uintptr_t>(ep->b)) & 15))
+                    return LLARK_EINVAL;
+                break;
+            case LLARK_EPI_SWIGLU_BWD:
+                // C is dgu [M, >= 2N] bf16, ep->a is gu with the same halves
+                if (c_fp32 || bias || R || !ep->a || (N % 8) || (ep->ld % 8) || ep->ld < 2LL * N || ldc < 2LL * N ||
+                    (reinterpret_cast<uintptr_t>(ep->a) & 15))
+                    return LLARK_EINVAL;
+                break;
+            default:
+                return LLARK_EINVAL;
+        }
+    }
     int rc = ensure_driver();
     if (rc != LLARK_OK) return rc;
     // TF32 operands are supported K-major only: MN-major 32-bit operands need the SWIZZLE_128B_BASE32B atom
@@ -891,6 +1008,12 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
     }
     p.a_tma4 = a4 ? use4 : 0;
     p.b_tma4 = b4 ? use4 : 0;
+    p.epi = ep ? ep->kind : 0;
+    p.epi_a = ep ? ep->a : nullptr;
+    p.epi_b = ep ? ep->b : nullptr;
+    p.epi_ld = ep ? ep->ld : 0;
+    p.epi_i0 = ep ? ep->i0 : 0;
+    p.epi_i1 = ep ? ep->i1 : 0;
     {
         static int dbg = -1;
         if (dbg < 0) {
@@ -901,6 +1024,22 @@ extern "C" int llark_gemm(const void* A, int a_mn_major, long long lda, const vo
     }
 
     const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+    if (p.epi != LLARK_EPI_NONE) {
+        // fused epilogues exist for the operand layouts their call sites use (validated above for everything else)
+        if (p.epi == LLARK_EPI_QUICK_GELU && sel == 0) {
+            if (two_cta) return in_fp32 ? launch2<0, 0, 1, 1>(ta, tb, p, max_ctas, stream)
+                                        : launch2<0, 0, 0, 1>(ta, tb, p, max_ctas, stream);
+            return in_fp32 ? launch<0, 0, 1, 1>(ta, tb, p, max_ctas, stream)
+                           : launch<0, 0, 0, 1>(ta, tb, p, max_ctas, stream);
+        }
+        if (p.epi == LLARK_EPI_ROPE && sel == 0 && !in_fp32)
+            return two_cta ? launch2<0, 0, 0, 2>(ta, tb, p, max_ctas, stream)
+                           : launch<0, 0, 0, 2>(ta, tb, p, max_ctas, stream);
+        if (p.epi == LLARK_EPI_SWIGLU_BWD && sel == 1 && !in_fp32)
+            return two_cta ? launch2<0, 1, 0, 3>(ta, tb, p, max_ctas, stream)
+                           : launch<0, 1, 0, 3>(ta, tb, p, max_ctas, stream);
+        return LLARK_EINVAL;
+    }
     if (two_cta) {
         if (!in_fp32) {
             switch (sel) {

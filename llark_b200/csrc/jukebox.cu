@@ -21,151 +21,198 @@ static inline int jb_check() {
     return LLARK_OK;
 }
 
-constexpr int TT = 128;  // output time positions per CTA
+// Register-tiled direct convolution from a shared-memory input tile. 256 threads = 8 warps; warp w owns the channel
+// group cg = w % NCG (CPT = COUT / NCG output channels) and the time group tg = w / NCG; lane l of it computes the
+// TPT output positions tg*32*TPT + l + 32*k. Weights sit in shared memory transposed to [ci][tap][co] so a thread
+// fetches its CPT channels with CPT/4 broadcast LDS.128 per tap: per input channel that is TPT*KT scalar LDS +
+// KT*CPT/4 LDS.128 against TPT*KT*CPT FMAs (>= 4 FMAs per shared-memory wavefront; the first version issued one
+// LDS per FMA and was MIO-bound at 29 % FMA utilisation, profiles/r1h_jukebox_full.md). The accumulation order
+// (bias, then ci ascending, taps ascending) is unchanged, so results are bit-identical to that version.
+template <int COUT, int KT, int STRIDE, int NCG, int TPT>
+struct ConvTile {
+    static constexpr int CPT = COUT / NCG;
+    static constexpr int TGROUPS = 8 / NCG;
+    static constexpr int TILE_T = TGROUPS * 32 * TPT;  // output positions per CTA
+    static_assert(CPT % 4 == 0 && 8 % NCG == 0, "tile shape");
+
+    // sx: [c_in][in_w] input tile whose column j holds the input needed by output position 0 tap 0 at j = 0.
+    // swT: [c_in][KT][COUT].
+    __device__ static __forceinline__ void run(const float* __restrict__ sx, int in_w, int dil,
+                                               const float* __restrict__ swT, int c_in,
+                                               const float* __restrict__ bias, float (&acc)[TPT][CPT], int& cg,
+                                               int& tl0) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        cg = warp % NCG;
+        tl0 = (warp / NCG) * (32 * TPT) + lane;
+#pragma unroll
+        for (int k = 0; k < TPT; ++k)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[k][c] = bias[cg * CPT + c];
+        for (int ci = 0; ci < c_in; ++ci) {
+            float xv[TPT][KT];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k)
+#pragma unroll
+                for (int j = 0; j < KT; ++j) xv[k][j] = sx[ci * in_w + (tl0 + 32 * k) * STRIDE + j * dil];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const float4* wp = reinterpret_cast<const float4*>(swT + (ci * KT + j) * COUT + cg * CPT);
+#pragma unroll
+                for (int c4 = 0; c4 < CPT / 4; ++c4) {
+                    const float4 w = wp[c4];
+#pragma unroll
+                    for (int k = 0; k < TPT; ++k) {
+                        acc[k][4 * c4 + 0] = fmaf(w.x, xv[k][j], acc[k][4 * c4 + 0]);
+                        acc[k][4 * c4 + 1] = fmaf(w.y, xv[k][j], acc[k][4 * c4 + 1]);
+                        acc[k][4 * c4 + 2] = fmaf(w.z, xv[k][j], acc[k][4 * c4 + 2]);
+                        acc[k][4 * c4 + 3] = fmaf(w.w, xv[k][j], acc[k][4 * c4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+};
+// Input tile [c_in][in_w] <- x[n, :, t_first + j] (zero outside [0, T)), optionally through ReLU. Eight independent
+// global loads are issued per thread before the first is consumed: the original one-load-then-store loop (with an
+// integer division per element) left a single load in flight per thread and was 36 % of the res-block's stall samples.
+template <bool RELU>
+__device__ __forceinline__ void load_x_tile(float* sx, const float* __restrict__ xn, int c_in, int T, int in_w,
+                                            int t_first) {
+    for (int j = threadIdx.x; j < in_w; j += blockDim.x) {
+        const int ti = t_first + j;
+        const bool ok = ti >= 0 && ti < T;
+        const float* src = xn + (ok ? ti : 0);
+        int ci = 0;
+        for (; ci + 8 <= c_in; ci += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ok ? src[(long long)(ci + u) * T] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sx[(ci + u) * in_w + j] = RELU ? fmaxf(v[u], 0.f) : v[u];
+        }
+        for (; ci < c_in; ++ci) {
+            const float v = ok ? src[(long long)ci * T] : 0.f;
+            sx[ci * in_w + j] = RELU ? fmaxf(v, 0.f) : v;
+        }
+    }
+}
+// global w [COUT][c_in][KT] -> shared [c_in][KT][COUT]
+template <int COUT, int KT>
+__device__ __forceinline__ void load_weights_T(float* swT, const float* __restrict__ w, int c_in) {
+    // consecutive threads write consecutive shared-memory words (conflict-free) and gather from global/L1: the
+    // transposing direction must be the read, a strided smem store is a COUT-way bank conflict
+    for (int i = threadIdx.x; i < COUT * c_in * KT; i += blockDim.x) {
+        const int r = i / COUT, co = i % COUT;  // r = ci*KT + k
+        swT[i] = w[co * (c_in * KT) + r];
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- down conv k4 s2 p1
-// y[n,co,t] = b[co] + sum_ci sum_k w[co,ci,k] * x[n,ci,2t-1+k].  256 threads = 128 t x 2 halves of c_out.
+// y[n,co,t] = b[co] + sum_ci sum_k w[co,ci,k] * x[n,ci,2t-1+k].
+template <int COUT>
+struct DownCfg {
+    using Tile = ConvTile<COUT, 4, 2, COUT / 16, 2>;
+};
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_down_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ y, int c_in, int T) {
-    extern __shared__ float sm[];
+    using Tile = typename DownCfg<COUT>::Tile;
+    extern __shared__ __align__(16) float sm[];
     const int To = T / 2;
     const int n = blockIdx.y;
-    const int t0 = blockIdx.x * TT;
-    const int in_w = 2 * TT + 2;
-    float* sx = sm;                        // [c_in][in_w]
-    float* sw = sm + c_in * in_w;          // [COUT][c_in][4]
-    for (int i = threadIdx.x; i < c_in * in_w; i += blockDim.x) {
-        const int ci = i / in_w, j = i % in_w;
-        const int ti = 2 * t0 - 1 + j;
-        sx[i] = (ti >= 0 && ti < T) ? x[((long long)n * c_in + ci) * T + ti] : 0.f;
-    }
-    for (int i = threadIdx.x; i < COUT * c_in * 4; i += blockDim.x) sw[i] = w[i];
+    const int t0 = blockIdx.x * Tile::TILE_T;
+    const int in_w = 2 * Tile::TILE_T + 2;
+    float* swT = sm;                         // [c_in][4][COUT]  (first: keeps it 16-byte aligned)
+    float* sx = sm + COUT * c_in * 4;        // [c_in][in_w]
+    load_x_tile<false>(sx, x + (long long)n * c_in * T, c_in, T, in_w, 2 * t0 - 1);
+    load_weights_T<COUT, 4>(swT, w, c_in);
     __syncthreads();
-    const int tl = threadIdx.x % TT, half = threadIdx.x / TT;
-    constexpr int CPT = COUT / 2;
-    float acc[CPT];
+    float acc[2][Tile::CPT];
+    int cg, tl0;
+    Tile::run(sx, in_w, 1, swT, c_in, bias, acc, cg, tl0);
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[c] = bias[half * CPT + c];
-    for (int ci = 0; ci < c_in; ++ci) {
-        const float* xr = sx + ci * in_w + 2 * tl;
-        const float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
+    for (int k = 0; k < 2; ++k) {
+        const int t = t0 + tl0 + 32 * k;
+        if (t < To) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const float* wr = sw + ((half * CPT + c) * c_in + ci) * 4;
-            acc[c] = fmaf(wr[0], x0, acc[c]);
-            acc[c] = fmaf(wr[1], x1, acc[c]);
-            acc[c] = fmaf(wr[2], x2, acc[c]);
-            acc[c] = fmaf(wr[3], x3, acc[c]);
+            for (int c = 0; c < Tile::CPT; ++c) y[((long long)n * COUT + cg * Tile::CPT + c) * To + t] = acc[k][c];
         }
-    }
-    const int t = t0 + tl;
-    if (t < To) {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) y[((long long)n * COUT + half * CPT + c) * To + t] = acc[c];
     }
 }
 
 // ---------------------------------------------------------------------------------------------- fused res block
 // y = x + W2 * relu(W1 (*dilation d, k=3) relu(x) + b1) + b2,   32 channels.
+using ResTile1 = ConvTile<32, 3, 1, 2, 2>;  // 256 output positions per CTA
+using ResTile2 = ConvTile<32, 1, 1, 2, 2>;
+constexpr int RES_TT = ResTile1::TILE_T;
 __global__ void __launch_bounds__(256)
 resblock_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
                 const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int T, int d) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     constexpr int C = 32;
     const int n = blockIdx.y;
-    const int t0 = blockIdx.x * TT;
-    const int in_w = TT + 2 * d;
-    float* sx = sm;                  // relu(x) tile [C][in_w]
-    float* sh = sx + C * in_w;       // relu(h) tile [C][TT]
-    float* sw1 = sh + C * TT;        // [C][C][3]
-    float* sw2 = sw1 + C * C * 3;    // [C][C]
-    for (int i = threadIdx.x; i < C * in_w; i += blockDim.x) {
-        const int ci = i / in_w, j = i % in_w;
-        const int ti = t0 - d + j;
-        const float v = (ti >= 0 && ti < T) ? x[((long long)n * C + ci) * T + ti] : 0.f;
-        sx[i] = fmaxf(v, 0.f);
-    }
-    for (int i = threadIdx.x; i < C * C * 3; i += blockDim.x) sw1[i] = w1[i];
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) sw2[i] = w2[i];
+    const int t0 = blockIdx.x * RES_TT;
+    const int in_w = RES_TT + 2 * d;
+    float* sw1T = sm;                  // [C][3][C]
+    float* sw2T = sw1T + C * C * 3;    // [C][C]
+    float* sh = sw2T + C * C;          // relu(h) tile [C][RES_TT]
+    float* sx = sh + C * RES_TT;       // relu(x) tile [C][in_w]
+    load_x_tile<true>(sx, x + (long long)n * C * T, C, T, in_w, t0 - d);
+    load_weights_T<C, 3>(sw1T, w1, C);
+    load_weights_T<C, 1>(sw2T, w2, C);
     __syncthreads();
-    const int tl = threadIdx.x % TT, half = threadIdx.x / TT;
-    constexpr int CPT = C / 2;
-    float acc[CPT];
+    float acc[2][ResTile1::CPT];
+    int cg, tl0;
+    ResTile1::run(sx, in_w, d, sw1T, C, b1, acc, cg, tl0);
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[c] = b1[half * CPT + c];
-    for (int ci = 0; ci < C; ++ci) {
-        const float* xr = sx + ci * in_w + tl;
-        const float x0 = xr[0], x1 = xr[d], x2 = xr[2 * d];
+    for (int k = 0; k < 2; ++k)
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const float* wr = sw1 + ((half * CPT + c) * C + ci) * 3;
-            acc[c] = fmaf(wr[0], x0, acc[c]);
-            acc[c] = fmaf(wr[1], x1, acc[c]);
-            acc[c] = fmaf(wr[2], x2, acc[c]);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) sh[(half * CPT + c) * TT + tl] = fmaxf(acc[c], 0.f);
+        for (int c = 0; c < ResTile1::CPT; ++c) sh[(cg * ResTile1::CPT + c) * RES_TT + tl0 + 32 * k] = fmaxf(acc[k][c], 0.f);
     __syncthreads();
+    ResTile2::run(sh, RES_TT, 1, sw2T, C, b2, acc, cg, tl0);
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[c] = b2[half * CPT + c];
-    for (int ci = 0; ci < C; ++ci) {
-        const float hv = sh[ci * TT + tl];
+    for (int k = 0; k < 2; ++k) {
+        const int t = t0 + tl0 + 32 * k;
+        if (t < T) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[c] = fmaf(sw2[(half * CPT + c) * C + ci], hv, acc[c]);
-    }
-    const int t = t0 + tl;
-    if (t < T) {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const long long off = ((long long)n * C + half * CPT + c) * T + t;
-            y[off] = x[off] + acc[c];
+            for (int c = 0; c < ResTile2::CPT; ++c) {
+                const long long off = ((long long)n * C + cg * ResTile2::CPT + c) * T + t;
+                y[off] = x[off] + acc[k][c];
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- conv k3 s1 p1
-// 256 threads = 64 t x 4 groups of c_out/4 channels.
+template <int COUT>
+struct K3Cfg {
+    using Tile = ConvTile<COUT, 3, 1, COUT / 16, 2>;
+};
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_k3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                float* __restrict__ y, int c_in, int T) {
-    extern __shared__ float sm[];
-    constexpr int TK = 64;
+    using Tile = typename K3Cfg<COUT>::Tile;
+    extern __shared__ __align__(16) float sm[];
     const int n = blockIdx.y;
-    const int t0 = blockIdx.x * TK;
-    const int in_w = TK + 2;
-    float* sx = sm;
-    float* sw = sm + c_in * in_w;  // [COUT][c_in][3]
-    for (int i = threadIdx.x; i < c_in * in_w; i += blockDim.x) {
-        const int ci = i / in_w, j = i % in_w;
-        const int ti = t0 - 1 + j;
-        sx[i] = (ti >= 0 && ti < T) ? x[((long long)n * c_in + ci) * T + ti] : 0.f;
-    }
-    for (int i = threadIdx.x; i < COUT * c_in * 3; i += blockDim.x) sw[i] = w[i];
+    const int t0 = blockIdx.x * Tile::TILE_T;
+    const int in_w = Tile::TILE_T + 2;
+    float* swT = sm;                       // [c_in][3][COUT]
+    float* sx = sm + COUT * c_in * 3;      // [c_in][in_w]
+    load_x_tile<false>(sx, x + (long long)n * c_in * T, c_in, T, in_w, t0 - 1);
+    load_weights_T<COUT, 3>(swT, w, c_in);
     __syncthreads();
-    const int tl = threadIdx.x % TK, grp = threadIdx.x / TK;
-    constexpr int CPT = COUT / 4;
-    float acc[CPT];
+    float acc[2][Tile::CPT];
+    int cg, tl0;
+    Tile::run(sx, in_w, 1, swT, c_in, bias, acc, cg, tl0);
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[c] = bias[grp * CPT + c];
-    for (int ci = 0; ci < c_in; ++ci) {
-        const float* xr = sx + ci * in_w + tl;
-        const float x0 = xr[0], x1 = xr[1], x2 = xr[2];
+    for (int k = 0; k < 2; ++k) {
+        const int t = t0 + tl0 + 32 * k;
+        if (t < T) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const float* wr = sw + ((grp * CPT + c) * c_in + ci) * 3;
-            acc[c] = fmaf(wr[0], x0, acc[c]);
-            acc[c] = fmaf(wr[1], x1, acc[c]);
-            acc[c] = fmaf(wr[2], x2, acc[c]);
+            for (int c = 0; c < Tile::CPT; ++c) y[((long long)n * COUT + cg * Tile::CPT + c) * T + t] = acc[k][c];
         }
-    }
-    const int t = t0 + tl;
-    if (t < T) {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) y[((long long)n * COUT + grp * CPT + c) * T + t] = acc[c];
     }
 }
 
@@ -366,6 +413,177 @@ jb_sparse_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------- factored attention, tensor cores
+// Same contract as jb_sparse_attn_kernel, on mma.sync m16n8k8 TF32 (fp32 accumulate): the SIMT kernel above issues one
+// shared-memory load per FMA and runs at ~6 TFLOP/s (4.7 ms per prior layer at batch 8, a third of the front end,
+// profiles/r1_session2_summary.md); here one CTA = one (group, head, n), each warp owns 16 query rows:
+//   S = Q K^T  (Q fragments in registers, K from shared memory, 19 k-steps of 8 over the 150(+2 zero) channels),
+//   softmax in registers on the accumulator fragments (quad shuffles),
+//   O = P V    with P taken straight from the S accumulators: the m16n8k8 A fragment wants key slots (t, t+4) where the
+//              accumulator holds keys (2t, 2t+1), so the k index of the P.V product is permuted consistently -- slot t
+//              reads V row 8j+2t, slot t+4 reads V row 8j+2t+1 -- and no shuffle is needed.
+// K and V rows are gathered (stride 1 or `blk`) into shared memory once per CTA; while S is computed the V tile
+// replaces the Q staging tile. Operands are rounded to TF32 (cvt.rna) when the fragments are formed. Causal key tiles
+// above the diagonal are skipped. Output fp32 or bf16 (fused cast for the bf16 prior).
+constexpr int JA_LD = 156;   // shared-memory row pitch (floats): 156 mod 32 = 28 -> conflict-free fragment loads
+constexpr int JA_KS = 19;    // k-steps of 8 covering head channels (<= 152)
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// rows x dh floats gathered from global (row r at base + (pos0 + r*stride)*rs) into smem [rows][JA_LD], pad columns zero
+__device__ __forceinline__ void ja_load_rows(float* dst, const float* __restrict__ base, long long pos0, int stride,
+                                             long long rs, int rows, int dh) {
+    constexpr int pairs = JA_LD / 2;  // float2 granules per row (dh is even, rows are 8-byte aligned)
+    const int total = rows * pairs;
+    // eight independent loads in flight per thread before the first shared-memory store
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int r = i / pairs, c = (i % pairs) * 2;
+            v[u] = make_float2(0.f, 0.f);
+            if (i < total && c < dh) v[u] = *reinterpret_cast<const float2*>(base + (pos0 + (long long)r * stride) * rs + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int r = i / pairs, c = (i % pairs) * 2;
+            if (i < total) *reinterpret_cast<float2*>(dst + r * JA_LD + c) = v[u];
+        }
+    }
+}
+template <int NKT>  // key tiles of 8 (8 -> 64 keys, 16 -> 128 keys)
+__global__ void __launch_bounds__(256)
+jb_sparse_attn_tc_kernel(const float* __restrict__ qkv, void* __restrict__ out, int out_bf16, int T, int heads, int dh,
+                         int blk, int pattern, float scale) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int NK = NKT * 8;
+    float* sK = sm;                 // [NK][JA_LD]
+    float* sV = sm + NK * JA_LD;    // [NK][JA_LD]  (first holds the Q tile)
+    const int g = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+    int qstride, q0, k0;
+    bool causal, has_keys = true;
+    if (pattern == 0) { qstride = 1; q0 = k0 = g * blk; causal = true; }
+    else if (pattern == 1) { qstride = blk; q0 = k0 = g; causal = true; }
+    else { qstride = 1; q0 = g * blk; k0 = (g - 1) * blk; causal = false; has_keys = g > 0; }
+    const long long rs = 3LL * heads * dh;
+    const long long ow = (long long)heads * dh;
+    const float* base = qkv + (long long)n * T * rs + (long long)h * dh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gq = lane >> 2, t4 = lane & 3;
+    const int r0 = warp * 16 + gq;  // this thread's rows inside the group: r0 and r0 + 8
+    if (!has_keys) {  // previous-block pattern, first block: no keys -> zeros (the SIMT kernel and the reference agree)
+        for (int i = threadIdx.x; i < NK * dh; i += blockDim.x) {
+            const long long pos = q0 + (long long)(i / dh) * qstride;
+            const long long o = ((long long)n * T + pos) * ow + (long long)h * dh + i % dh;
+            if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(0.f);
+            else reinterpret_cast<float*>(out)[o] = 0.f;
+        }
+        return;
+    }
+    ja_load_rows(sK, base + (long long)heads * dh, k0, qstride, rs, NK, dh);
+    ja_load_rows(sV, base, q0, qstride, rs, NK, dh);  // Q staged in the V buffer
+    __syncthreads();
+    uint32_t qa[JA_KS][4];
+#pragma unroll
+    for (int ks = 0; ks < JA_KS; ++ks) {
+        qa[ks][0] = to_tf32(sV[r0 * JA_LD + ks * 8 + t4]);
+        qa[ks][1] = to_tf32(sV[(r0 + 8) * JA_LD + ks * 8 + t4]);
+        qa[ks][2] = to_tf32(sV[r0 * JA_LD + ks * 8 + t4 + 4]);
+        qa[ks][3] = to_tf32(sV[(r0 + 8) * JA_LD + ks * 8 + t4 + 4]);
+    }
+    __syncthreads();  // every warp holds its Q fragments: the buffer may now receive V
+    ja_load_rows(sV, base + 2LL * heads * dh, k0, qstride, rs, NK, dh);
+    // key tiles this warp needs: causal rows 16w .. 16w+15 see keys <= 16w+15
+    const int nt_end = causal ? min(NKT, 2 * warp + 2) : NKT;
+    float sc[NKT][4];
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt) {
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+        if (nt < nt_end) {
+            const float* kr = sK + (nt * 8 + gq) * JA_LD + t4;
+#pragma unroll
+            for (int ks = 0; ks < JA_KS; ++ks) mma_tf32(sc[nt], qa[ks], to_tf32(kr[ks * 8]), to_tf32(kr[ks * 8 + 4]));
+        }
+    }
+    // softmax over the keys of rows r0 (elements 0,1) and r0+8 (elements 2,3)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int key = nt * 8 + 2 * t4 + (e & 1);
+            const int row = r0 + (e >> 1) * 8;
+            const bool ok = nt < nt_end && (!causal || key <= row);
+            const float v = ok ? sc[nt][e] * scale : -INFINITY;
+            sc[nt][e] = v;
+            mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = (sc[nt][e] == -INFINITY) ? 0.f : __expf(sc[nt][e] - mx[e >> 1]);
+            sc[nt][e] = p;
+            sum[e >> 1] += p;
+        }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+    }
+    __syncthreads();  // V tile complete in shared memory
+    float oacc[JA_KS][4];
+#pragma unroll
+    for (int nn = 0; nn < JA_KS; ++nn) oacc[nn][0] = oacc[nn][1] = oacc[nn][2] = oacc[nn][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NKT; ++j) {
+        if (j < nt_end) {
+            uint32_t pa[4];
+            pa[0] = to_tf32(sc[j][0]);  // (row r0,   key 8j+2t)   -> k slot t
+            pa[1] = to_tf32(sc[j][2]);  // (row r0+8, key 8j+2t)
+            pa[2] = to_tf32(sc[j][1]);  // (row r0,   key 8j+2t+1) -> k slot t+4
+            pa[3] = to_tf32(sc[j][3]);
+            const float* v0 = sV + (j * 8 + 2 * t4) * JA_LD + gq;
+#pragma unroll
+            for (int nn = 0; nn < JA_KS; ++nn) mma_tf32(oacc[nn], pa, to_tf32(v0[nn * 8]), to_tf32(v0[JA_LD + nn * 8]));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float inv = sum[r] > 0.f ? 1.f / sum[r] : 0.f;
+        const long long pos = q0 + (long long)(r0 + r * 8) * qstride;
+        const long long o = ((long long)n * T + pos) * ow + (long long)h * dh;
+#pragma unroll
+        for (int nn = 0; nn < JA_KS; ++nn) {
+            const int col = nn * 8 + 2 * t4;
+            if (col < dh) {
+                const float a = oacc[nn][2 * r] * inv, b = oacc[nn][2 * r + 1] * inv;
+                if (out_bf16)
+                    *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + o + col) = pack_bf16x2(a, b);
+                else
+                    *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + o + col) = make_float2(a, b);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- elementwise
 __global__ void quick_gelu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -424,14 +642,18 @@ using namespace llark;
 extern "C" int llark_jb_conv_down(const float* x, const float* w, const float* bias, float* y, int N, int c_in,
                                   int c_out, int T, cudaStream_t st) {
     if (N <= 0 || T <= 0 || (T & 1) || c_in <= 0 || (c_out != 32 && c_out != 64)) return LLARK_EINVAL;
-    const int smem = (c_in * (2 * TT + 2) + c_out * c_in * 4) * (int)sizeof(float);
-    dim3 grid((T / 2 + TT - 1) / TT, N);
     int rc;
     if (c_out == 32) {
+        constexpr int TILE = DownCfg<32>::Tile::TILE_T;
+        const int smem = (c_in * (2 * TILE + 2) + c_out * c_in * 4) * (int)sizeof(float);
+        dim3 grid((T / 2 + TILE - 1) / TILE, N);
         rc = set_dyn_smem((const void*)conv_down_kernel<32>, smem);
         if (rc) return rc;
         conv_down_kernel<32><<<grid, 256, smem, st>>>(x, w, bias, y, c_in, T);
     } else {
+        constexpr int TILE = DownCfg<64>::Tile::TILE_T;
+        const int smem = (c_in * (2 * TILE + 2) + c_out * c_in * 4) * (int)sizeof(float);
+        dim3 grid((T / 2 + TILE - 1) / TILE, N);
         rc = set_dyn_smem((const void*)conv_down_kernel<64>, smem);
         if (rc) return rc;
         conv_down_kernel<64><<<grid, 256, smem, st>>>(x, w, bias, y, c_in, T);
@@ -442,10 +664,10 @@ extern "C" int llark_jb_conv_down(const float* x, const float* w, const float* b
 extern "C" int llark_jb_resblock(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                  float* y, int N, int T, int dilation, cudaStream_t st) {
     if (N <= 0 || T <= 0 || dilation < 1 || dilation > 243) return LLARK_EINVAL;
-    const int smem = (32 * (TT + 2 * dilation) + 32 * TT + 32 * 32 * 3 + 32 * 32) * (int)sizeof(float);
+    const int smem = (32 * (RES_TT + 2 * dilation) + 32 * RES_TT + 32 * 32 * 3 + 32 * 32) * (int)sizeof(float);
     int rc = set_dyn_smem((const void*)resblock_kernel, smem);
     if (rc) return rc;
-    dim3 grid((T + TT - 1) / TT, N);
+    dim3 grid((T + RES_TT - 1) / RES_TT, N);
     resblock_kernel<<<grid, 256, smem, st>>>(x, w1, b1, w2, b2, y, T, dilation);
     return jb_check();
 }
@@ -453,14 +675,18 @@ extern "C" int llark_jb_resblock(const float* x, const float* w1, const float* b
 extern "C" int llark_jb_conv_k3(const float* x, const float* w, const float* bias, float* y, int N, int c_in, int c_out,
                                 int T, cudaStream_t st) {
     if (N <= 0 || T <= 0 || c_in <= 0 || (c_out != 32 && c_out != 64)) return LLARK_EINVAL;
-    const int smem = (c_in * 66 + c_out * c_in * 3) * (int)sizeof(float);
-    dim3 grid((T + 63) / 64, N);
     int rc;
     if (c_out == 64) {
+        constexpr int TILE = K3Cfg<64>::Tile::TILE_T;
+        const int smem = (c_in * (TILE + 2) + c_out * c_in * 3) * (int)sizeof(float);
+        dim3 grid((T + TILE - 1) / TILE, N);
         rc = set_dyn_smem((const void*)conv_k3_kernel<64>, smem);
         if (rc) return rc;
         conv_k3_kernel<64><<<grid, 256, smem, st>>>(x, w, bias, y, c_in, T);
     } else {
+        constexpr int TILE = K3Cfg<32>::Tile::TILE_T;
+        const int smem = (c_in * (TILE + 2) + c_out * c_in * 3) * (int)sizeof(float);
+        dim3 grid((T + TILE - 1) / TILE, N);
         rc = set_dyn_smem((const void*)conv_k3_kernel<32>, smem);
         if (rc) return rc;
         conv_k3_kernel<32><<<grid, 256, smem, st>>>(x, w, bias, y, c_in, T);
@@ -503,6 +729,31 @@ extern "C" int llark_jb_sparse_attn(const float* qkv, float* out, int N, int T, 
     if (rc) return rc;
     dim3 grid(groups, heads, N);
     jb_sparse_attn_kernel<<<grid, 256, smem, st>>>(qkv, out, T, heads, dh, block, pattern, 1.f / sqrtf((float)dh));
+    return jb_check();
+}
+
+// Tensor-core variant (TF32 operands, fp32 accumulate); out fp32 or bf16. LLARK_EINVAL when the geometry is outside
+// its envelope (64- or 128-row groups, even head width <= 152): callers then use llark_jb_sparse_attn.
+extern "C" int llark_jb_sparse_attn_tc(const float* qkv, void* out, int out_bf16, int N, int T, int heads, int dh,
+                                       int block, int pattern, cudaStream_t st) {
+    if (N <= 0 || T <= 0 || block <= 0 || T % block || pattern < 0 || pattern > 2) return LLARK_EINVAL;
+    const int nblk = T / block;
+    const int rows = (pattern == 1) ? nblk : block;  // queries (= keys) per group
+    if ((rows != 64 && rows != 128) || dh > 8 * JA_KS || (dh & 1)) return LLARK_EINVAL;
+    const int groups = (pattern == 1) ? block : nblk;
+    const int smem = 2 * rows * JA_LD * (int)sizeof(float);
+    dim3 grid(groups, heads, N);
+    const float scale = 1.f / sqrtf((float)dh);
+    int rc;
+    if (rows == 64) {
+        rc = set_dyn_smem((const void*)jb_sparse_attn_tc_kernel<8>, smem);
+        if (rc) return rc;
+        jb_sparse_attn_tc_kernel<8><<<grid, 128, smem, st>>>(qkv, out, out_bf16, T, heads, dh, block, pattern, scale);
+    } else {
+        rc = set_dyn_smem((const void*)jb_sparse_attn_tc_kernel<16>, smem);
+        if (rc) return rc;
+        jb_sparse_attn_tc_kernel<16><<<grid, 256, smem, st>>>(qkv, out, out_bf16, T, heads, dh, block, pattern, scale);
+    }
     return jb_check();
 }
 

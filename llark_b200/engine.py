@@ -14,6 +14,7 @@ non-ignored shifted tokens computed on bf16 logits, lm_head frozen when requires
 embedding rows detached when `orig_embeds_params` is set (m2t/models/llamav2.py:176-198).
 """
 import math
+import os
 
 import torch
 
@@ -146,6 +147,9 @@ class LlamaEngine:
         self.flags = None  # device int32[1]: splice validation bits (see llark_splice_scan)
         self.launches = 0  # kernels launched by the last forward(+backward): bench.py's gpu_launches
         self.comm_chunk_layers = 4
+        # RoPE and SwiGLU-backward fused into GEMM epilogues (llark_gemm_ex); LLARK_FUSE_EPILOGUES=0 keeps the
+        # separate llark_rope / llark_swiglu_bwd kernels (same results bit for bit)
+        self.fuse_epilogues = os.environ.get("LLARK_FUSE_EPILOGUES", "1") != "0"
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -268,8 +272,13 @@ class LlamaEngine:
             Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
             rstd1 = torch.empty(M, device=dev, dtype=torch.float32)
             xn1 = ops.rmsnorm_fwd(x, w_in, eps, rstd=rstd1)
-            qkv = ops.gemm(xn1, Wqkv)
-            ops.rope_(qkv, cos, sin, S, NH, D)
+            if self.fuse_epilogues and D == 128:
+                # RoPE of the q | k heads in the QKV projection's epilogue (bit-identical to gemm -> llark_rope)
+                qkv = ops.gemm(xn1, Wqkv, rope=(cos, sin, S, 2 * H))
+            else:
+                qkv = ops.gemm(xn1, Wqkv)
+                ops.rope_(qkv, cos, sin, S, NH, D)
+                n0 += 1
             attn, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
             x_mid = ops.gemm(attn, Wo, residual=x)
             rstd2 = torch.empty(M, device=dev, dtype=torch.float32)
@@ -277,7 +286,7 @@ class LlamaEngine:
             gu = ops.gemm(xn2, Wgu)
             act = ops.swiglu_fwd(gu)
             x_out = ops.gemm(act, Wd, residual=x_mid)
-            n0 += 9
+            n0 += 8
             if need_grad:
                 saved["layers"].append((x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act))
             x = x_out
@@ -364,12 +373,19 @@ class LlamaEngine:
             Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
             Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
             # MLP
-            dact = ops.gemm(dx, Wd, b_mn=True)  # [M,I] = dx[M,H] @ Wd[H,I]
-            n0 += 1 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
-            dgu = ops.swiglu_bwd(gu, dact)
-            del dact
+            if self.fuse_epilogues:
+                # d(act)[M,I] = dx[M,H] @ Wd[H,I] never reaches HBM: the dgrad's epilogue applies the SwiGLU backward
+                # and writes dgu = (dgate | dup) directly (bit-identical to gemm -> llark_swiglu_bwd)
+                dgu = torch.empty_like(gu)
+                ops.gemm(dx, Wd, b_mn=True, out=dgu, N=I, swiglu_bwd=gu)
+                n0 += 1 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
+            else:
+                dact = ops.gemm(dx, Wd, b_mn=True)  # [M,I] = dx[M,H] @ Wd[H,I]
+                n0 += 2 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
+                dgu = ops.swiglu_bwd(gu, dact)
+                del dact
             dxn2 = ops.gemm(dgu, Wgu, b_mn=True)  # [M,H] = dgu[M,2I] @ Wgu[2I,H]
-            n0 += 2 + wgrad(pfx + "mlp.gate_proj.weight", dgu, xn2, (2 * I, H), span=2)
+            n0 += 1 + wgrad(pfx + "mlp.gate_proj.weight", dgu, xn2, (2 * I, H), span=2)
             del dgu
             dx_mid = torch.empty((M, H), device=dev, dtype=BF16)
             ops.rmsnorm_bwd(x_mid, flat.pview(pfx + "post_attention_layernorm.weight"), dxn2, rstd2, dx, dx_mid,

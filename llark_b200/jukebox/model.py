@@ -184,14 +184,13 @@ class PriorTransformer:
             q = f"blk.{d}"
             n0 = ops.layernorm_fwd(h, w[q + ".ln0.g"], w[q + ".ln0.b"], cfg.ln_eps, out_dtype=act_dt)
             qkv = self._lin(n0, q + ".c_attn")
-            a = ops.jb_sparse_attn(qkv, N, T, cfg.heads, dh, bc, d % 3)
-            if act_dt == BF16:
+            a = ops.jb_sparse_attn(qkv, N, T, cfg.heads, dh, bc, d % 3, out_dtype=act_dt)  # cast fused (bf16 prior)
+            if a.dtype != act_dt:
                 a = ops.cast_f32_to_bf16(a)
             xa = self._lin(a, q + ".c_proj", residual=h)  # x + a
             n1 = ops.layernorm_fwd(xa, w[q + ".ln1.g"], w[q + ".ln1.b"], cfg.ln_eps, out_dtype=act_dt)
-            m = ops.quick_gelu(self._lin(n1, q + ".fc"))
-            if act_dt == BF16:
-                m = ops.cast_f32_to_bf16(m)
+            # quick-GELU (and the bf16 cast of the bf16 prior) fused into the fc GEMM's epilogue
+            m = ops.gemm(n1, w[q + ".fc.w"], bias=w[q + ".fc.b"], out_dtype=act_dt, quick_gelu=True)
             h = self._lin(m, q + ".fc_proj", residual=xa)  # (x + a) + m
         return h.view(N, T, cfg.prior_width)
 

@@ -9,7 +9,7 @@ import math
 
 import torch
 
-from ._lib import check, lib
+from ._lib import EPI_QUICK_GELU, EPI_ROPE, EPI_SWIGLU_BWD, GemmEpilogue, check, lib
 
 BF16 = torch.bfloat16
 
@@ -35,8 +35,13 @@ def _req(t, dtype=None):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_dtype=None, bias=None,
-         residual=None, lda=None, ldb=None, ldc=None, ldr=None, max_ctas=0):
-    """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (+residual).
+         residual=None, lda=None, ldb=None, ldc=None, ldr=None, max_ctas=0, quick_gelu=False, rope=None,
+         swiglu_bwd=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias) (+residual), optionally with one fused epilogue (llark_gemm_ex):
+
+    quick_gelu=True            C = quick_gelu(acc + bias)
+    rope=(cos, sin, S, cols)   columns [0, cols) rotated per 128-wide head, position = row % S (fused-QKV projection)
+    swiglu_bwd=gu              acc is d(act) [M, I]; `out` must be the dgu buffer [M, 2I]: out = (dgate | dup)
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True); row-major with
     leading dimension = last-dim stride unless lda/ldb given. bf16 inputs use kind::f16, fp32 inputs kind::tf32.
@@ -69,8 +74,21 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = lib().llark_gemm(_p(a), int(a_mn), lda, _p(b), int(b_mn), ldb, _p(out), ldc, int(c_fp32), _p(bias),
-                          int(bias_fp32), _p(residual), ldr, M, N, K, int(in_fp32), max_ctas, _stream())
+    ep = None
+    if quick_gelu:
+        ep = GemmEpilogue(EPI_QUICK_GELU, None, None, 0, 0, 0)
+    elif rope is not None:
+        cos_t, sin_t, S_rope, cols = rope
+        ep = GemmEpilogue(EPI_ROPE, cos_t.data_ptr(), sin_t.data_ptr(), 0, int(S_rope), int(cols))
+    elif swiglu_bwd is not None:
+        ep = GemmEpilogue(EPI_SWIGLU_BWD, swiglu_bwd.data_ptr(), None, swiglu_bwd.stride(0), 0, 0)
+    if ep is None:
+        rc = lib().llark_gemm(_p(a), int(a_mn), lda, _p(b), int(b_mn), ldb, _p(out), ldc, int(c_fp32), _p(bias),
+                              int(bias_fp32), _p(residual), ldr, M, N, K, int(in_fp32), max_ctas, _stream())
+    else:
+        rc = lib().llark_gemm_ex(_p(a), int(a_mn), lda, _p(b), int(b_mn), ldb, _p(out), ldc, int(c_fp32), _p(bias),
+                                 int(bias_fp32), _p(residual), ldr, M, N, K, int(in_fp32), max_ctas, ctypes.byref(ep),
+                                 _stream())
     check(rc, f"llark_gemm(M={M},N={N},K={K})")
     if prof is not None:
         e1.record()
@@ -246,8 +264,22 @@ def jb_embed_tokens(codes, emb, y_cond, pos_emb, x_cond):
     return out
 
 
-def jb_sparse_attn(qkv, N, T, heads, dh, block, pattern, out=None):
-    out = out if out is not None else torch.empty((N * T, heads * dh), device=qkv.device, dtype=torch.float32)
+def jb_sparse_attn(qkv, N, T, heads, dh, block, pattern, out=None, out_dtype=torch.float32, exact=False):
+    """Factored attention of the prior. Default: the tensor-core kernel (TF32 operands, fp32 accumulate, fp32 or bf16
+    output); exact=True (or a geometry outside that kernel's envelope) runs the fp32 SIMT kernel (fp32 output)."""
+    own = out is None
+    if own:
+        out = torch.empty((N * T, heads * dh), device=qkv.device, dtype=torch.float32 if exact else out_dtype)
+    if not exact:
+        rc = lib().llark_jb_sparse_attn_tc(_p(qkv), _p(out), int(out.dtype == BF16), N, T, heads, dh, block, pattern,
+                                           _stream())
+        if rc != -1:  # LLARK_EINVAL = outside the envelope -> SIMT kernel below
+            check(rc, "jb_sparse_attn_tc")
+            return out
+        if out.dtype != torch.float32:
+            if not own:
+                raise TypeError("the SIMT factored-attention kernel writes fp32")
+            out = torch.empty((N * T, heads * dh), device=qkv.device, dtype=torch.float32)  # caller casts
     check(lib().llark_jb_sparse_attn(_p(qkv), _p(out), N, T, heads, dh, block, pattern, _stream()), "jb_sparse_attn")
     return out
 

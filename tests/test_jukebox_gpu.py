@@ -84,8 +84,32 @@ def test_sparse_attention_real_head_shape(pattern):
     g = torch.Generator().manual_seed(pattern)
     qkv = torch.randn(1, 2048, 3 * cfg.attn_width, generator=g)
     ref = jo.factored_attention(qkv, cfg, pattern)
-    out = ops.jb_sparse_attn(qkv.view(2048, -1).cuda().contiguous(), 1, 2048, 8, 150, 64, pattern)
+    q = qkv.view(2048, -1).cuda().contiguous()
+    out = ops.jb_sparse_attn(q, 1, 2048, 8, 150, 64, pattern, exact=True)  # fp32 SIMT kernel
     assert _rel(out.view(1, 2048, -1), ref) < 1e-4
+    # tensor-core kernel: operands rounded to TF32 (10-bit mantissa), fp32 accumulate -> 2e-3; bf16 output adds 2^-9
+    out_tc = ops.jb_sparse_attn(q, 1, 2048, 8, 150, 64, pattern)
+    assert out_tc.dtype == torch.float32 and _rel(out_tc.view(1, 2048, -1), ref) < 2e-3
+    out_bf = ops.jb_sparse_attn(q, 1, 2048, 8, 150, 64, pattern, out_dtype=torch.bfloat16)
+    if pattern == 1:
+        # 32 blocks -> 32-row groups: outside the tensor-core kernel's envelope (64 / 128 rows), so the wrapper ran the
+        # fp32 SIMT kernel and hands back fp32 for the caller to cast
+        assert out_bf.dtype == torch.float32 and torch.equal(out_bf, out)
+    else:
+        assert out_bf.dtype == torch.bfloat16 and _rel(out_bf.view(1, 2048, -1), ref) < 5e-3
+        assert torch.equal(out_bf, out_tc.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("pattern", [0, 1, 2])
+def test_sparse_attention_tc_full_geometry(pattern):
+    """T = 8192, 128 blocks of 64 (the real prior): pattern 1 gathers 128-row groups with stride 64."""
+    from llark_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(10 + pattern)
+    qkv = torch.randn(2 * 8192, 3600, device="cuda", generator=g)
+    ref = ops.jb_sparse_attn(qkv, 2, 8192, 8, 150, 64, pattern, exact=True)
+    got = ops.jb_sparse_attn(qkv, 2, 8192, 8, 150, 64, pattern)
+    assert _rel(got, ref) < 2e-3
 
 
 def test_pool_matches_reference_golden():

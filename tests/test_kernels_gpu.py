@@ -216,6 +216,52 @@ def test_swiglu_fwd_bwd():
     assert _rel(dgu[:, I:], u.grad) < 5e-3
 
 
+# ------------------------------------------------------------------------------------------------ fused GEMM epilogues
+def test_gemm_rope_epilogue_is_bit_identical_to_gemm_then_rope(gemm_mode):
+    """llark_gemm_ex(LLARK_EPI_ROPE) == llark_gemm followed by llark_rope, bit for bit (q | k rotated, v untouched)."""
+    ops = _ops()
+    torch.manual_seed(21)
+    B, S, NH, D, K = 3, 100, 2, 128, 320
+    H = NH * D
+    x = (torch.randn(B * S, K, device="cuda") * 0.5).to(BF16)
+    w = (torch.randn(3 * H, K, device="cuda") * 0.1).to(BF16)
+    cos, sin = _hf_rope_tables(S, D)
+    ref = ops.gemm(x, w)
+    ops.rope_(ref, cos, sin, S, NH, D)
+    got = ops.gemm(x, w, rope=(cos, sin, S, 2 * H))
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("M,I,H", [(300, 344, 256), (256, 11008, 128)])
+def test_gemm_swiglu_bwd_epilogue_is_bit_identical(M, I, H, gemm_mode):
+    """dgrad of the down projection with the SwiGLU backward in its epilogue == gemm -> llark_swiglu_bwd."""
+    ops = _ops()
+    torch.manual_seed(22)
+    dx = (torch.randn(M, H, device="cuda") * 0.5).to(BF16)
+    wd = (torch.randn(H, I, device="cuda") * 0.1).to(BF16)  # down_proj.weight [H, I]
+    gu = torch.randn(M, 2 * I, device="cuda").to(BF16)
+    dact = ops.gemm(dx, wd, b_mn=True)
+    ref = ops.swiglu_bwd(gu, dact)
+    got = torch.full_like(gu, float("nan"))
+    ops.gemm(dx, wd, b_mn=True, out=got, N=I, swiglu_bwd=gu)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, BF16])
+def test_gemm_quick_gelu_epilogue_is_bit_identical(dt, gemm_mode):
+    ops = _ops()
+    torch.manual_seed(23)
+    M, N, K = 200, 520, 192
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(BF16)
+    w = (torch.randn(N, K, device="cuda") * 0.2).to(BF16)
+    bias = torch.randn(N, device="cuda")
+    ref = ops.quick_gelu(ops.gemm(x, w, bias=bias, out_dtype=torch.float32))
+    if dt == BF16:
+        ref = ops.cast_f32_to_bf16(ref)
+    got = ops.gemm(x, w, bias=bias, out_dtype=dt, quick_gelu=True)
+    assert torch.equal(got, ref)
+
+
 def _attn_ref(qkv, mask, B, S, NH, D):
     q, k, v = qkv.float().view(B, S, 3, NH, D).permute(2, 0, 3, 1, 4)
     sc = (q @ k.transpose(-1, -2)) / math.sqrt(D)
