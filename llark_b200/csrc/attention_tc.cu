@@ -369,7 +369,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
 // the backward pass, so the split is free). S and dP are double-buffered in TMEM: the KK MMAs of tile t+1 run while
 // the compute warps work on tile t. One CTA per SM (145-162 KB of shared memory, all 512 TMEM columns).
 constexpr int kBwdThreads = 320;
-constexpr int RING_SLOTS = 4;
+constexpr int RING_SLOTS = 6;   // three streamed tiles in flight: with 4 the load of tile j+2 could only be requested after
+                                // tile j's last MMA retired, and its latency sat on the critical path of every tile
+__device__ __forceinline__ int ring_slot(int it) { return it % RING_SLOTS; }
+__device__ __forceinline__ uint32_t ring_phase(int it) { return (uint32_t)(it / RING_SLOTS) & 1u; }
 
 __device__ __forceinline__ void mma_kk_128x64(uint32_t tD, uint32_t a_addr, uint32_t a_chunk_bytes, uint32_t b_addr,
                                               uint32_t b_chunk_bytes, uint32_t idesc) {
@@ -444,8 +447,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     uint8_t* sdS = smem + DQ_OFF_DS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_OFF_BAR);
     uint64_t* q_full = bars;                       // [1]  Q and dO tiles landed
-    uint64_t* ring_full = bars + 1;                // [4]
-    uint64_t* ring_empty = ring_full + RING_SLOTS; // [4]
+    uint64_t* ring_full = bars + 1;                // [RING_SLOTS]
+    uint64_t* ring_empty = ring_full + RING_SLOTS; // [RING_SLOTS]
     uint64_t* sdp_full = ring_empty + RING_SLOTS;  // [2]  S and dP of tile j are in TMEM
     uint64_t* sdp_empty = sdp_full + 2;            // [2]  8 compute warps have read them
     uint64_t* ds_full = sdp_empty + 2;             // [2]  dS tile j written to shared-memory buffer j & 1
@@ -501,8 +504,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             for (int j = 0; j < n_kv; ++j) {
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv) {
-                    const int it = 2 * j + kv, slot = it & 3;
-                    mbar_wait(&ring_empty[slot], (((uint32_t)it >> 2) & 1) ^ 1);
+                    const int it = 2 * j + kv, slot = ring_slot(it);
+                    mbar_wait(&ring_empty[slot], ring_phase(it) ^ 1);
                     uint8_t* dst = sRing + slot * KV_BYTES;
                     mbar_arrive_expect_tx(&ring_full[slot], KV_BYTES);
                     const int col = kv ? cv : ck;
@@ -521,15 +524,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 const int sb = j & 1;
                 const int itk = 2 * j, itv = 2 * j + 1;
                 mbar_wait(&sdp_empty[sb], ((uint32_t)(j >> 1) & 1) ^ 1);
-                mbar_wait(&ring_full[itk & 3], ((uint32_t)itk >> 2) & 1);
+                mbar_wait(&ring_full[ring_slot(itk)], ring_phase(itk));
                 tc_fence_after();
-                mma_kk_128x64(tmem_base + sb * BK, smem_u32(sQ), BQ * 128, smem_u32(sRing + (itk & 3) * KV_BYTES),
+                mma_kk_128x64(tmem_base + sb * BK, smem_u32(sQ), BQ * 128, smem_u32(sRing + ring_slot(itk) * KV_BYTES),
                               BK * 128, idesc_kk);
-                mbar_wait(&ring_full[itv & 3], ((uint32_t)itv >> 2) & 1);
+                mbar_wait(&ring_full[ring_slot(itv)], ring_phase(itv));
                 tc_fence_after();
                 mma_kk_128x64(tmem_base + 128 + sb * BK, smem_u32(sdO), BQ * 128,
-                              smem_u32(sRing + (itv & 3) * KV_BYTES), BK * 128, idesc_kk);
-                umma_commit(&ring_empty[itv & 3]);  // V_j is not needed again
+                              smem_u32(sRing + ring_slot(itv) * KV_BYTES), BK * 128, idesc_kk);
+                umma_commit(&ring_empty[ring_slot(itv)]);  // V_j is not needed again
                 umma_commit(&sdp_full[sb]);
             };
             mbar_wait(q_full, 0);
@@ -540,8 +543,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 tc_fence_after();
                 const int itk = 2 * j;
                 mma_pv_128x128(tmem_base + 256, smem_u32(sdS + (j & 1) * P_BYTES),
-                               smem_u32(sRing + (itk & 3) * KV_BYTES), idesc_pv, j != 0);
-                umma_commit(&ring_empty[itk & 3]);
+                               smem_u32(sRing + ring_slot(itk) * KV_BYTES), idesc_pv, j != 0);
+                umma_commit(&ring_empty[ring_slot(itk)]);
                 umma_commit(&dq_done[j & 1]);
             }
         }
@@ -636,8 +639,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint8_t* sdST = smem + KV_OFF_DST;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + KV_OFF_BAR);
     uint64_t* kv_full = bars;                      // [1]
-    uint64_t* ring_full = bars + 1;                // [4]
-    uint64_t* ring_empty = ring_full + RING_SLOTS; // [4]
+    uint64_t* ring_full = bars + 1;                // [RING_SLOTS]
+    uint64_t* ring_empty = ring_full + RING_SLOTS; // [RING_SLOTS]
     uint64_t* sdp_full = ring_empty + RING_SLOTS;  // [2]
     uint64_t* sdp_empty = sdp_full + 2;            // [2]
     uint64_t* pds_full = sdp_empty + 2;            // [2]  P^T and dS^T of tile t written to buffers t & 1
@@ -695,8 +698,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 const int qrow = row0 + (t0 + t) * BK;
 #pragma unroll
                 for (int which = 0; which < 2; ++which) {  // 0: Q_t, 1: dO_t
-                    const int it = 2 * t + which, slot = it & 3;
-                    mbar_wait(&ring_empty[slot], (((uint32_t)it >> 2) & 1) ^ 1);
+                    const int it = 2 * t + which, slot = ring_slot(it);
+                    mbar_wait(&ring_empty[slot], ring_phase(it) ^ 1);
                     uint8_t* dst = sRing + slot * KV_BYTES;
                     mbar_arrive_expect_tx(&ring_full[slot], KV_BYTES);
                     const CUtensorMap* tm = which ? &tm_do : &tm_qkv;
@@ -715,14 +718,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 const int sb = t & 1;
                 const int itq = 2 * t, itd = 2 * t + 1;
                 mbar_wait(&sdp_empty[sb], ((uint32_t)(t >> 1) & 1) ^ 1);
-                mbar_wait(&ring_full[itq & 3], ((uint32_t)itq >> 2) & 1);
+                mbar_wait(&ring_full[ring_slot(itq)], ring_phase(itq));
                 tc_fence_after();
-                mma_kk_128x64(tmem_base + sb * BK, smem_u32(sK), BQ * 128, smem_u32(sRing + (itq & 3) * KV_BYTES),
+                mma_kk_128x64(tmem_base + sb * BK, smem_u32(sK), BQ * 128, smem_u32(sRing + ring_slot(itq) * KV_BYTES),
                               BK * 128, idesc_kk);
-                mbar_wait(&ring_full[itd & 3], ((uint32_t)itd >> 2) & 1);
+                mbar_wait(&ring_full[ring_slot(itd)], ring_phase(itd));
                 tc_fence_after();
                 mma_kk_128x64(tmem_base + 128 + sb * BK, smem_u32(sV), BQ * 128,
-                              smem_u32(sRing + (itd & 3) * KV_BYTES), BK * 128, idesc_kk);
+                              smem_u32(sRing + ring_slot(itd) * KV_BYTES), BK * 128, idesc_kk);
                 umma_commit(&sdp_full[sb]);
             };
             mbar_wait(kv_full, 0);
@@ -733,11 +736,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 tc_fence_after();
                 const int itq = 2 * t, itd = 2 * t + 1;
                 mma_pv_128x128(tmem_base + 256, smem_u32(sPT + (t & 1) * P_BYTES),
-                               smem_u32(sRing + (itd & 3) * KV_BYTES), idesc_pv, t != 0);
-                umma_commit(&ring_empty[itd & 3]);
+                               smem_u32(sRing + ring_slot(itd) * KV_BYTES), idesc_pv, t != 0);
+                umma_commit(&ring_empty[ring_slot(itd)]);
                 mma_pv_128x128(tmem_base + 384, smem_u32(sdST + (t & 1) * P_BYTES),
-                               smem_u32(sRing + (itq & 3) * KV_BYTES), idesc_pv, t != 0);
-                umma_commit(&ring_empty[itq & 3]);
+                               smem_u32(sRing + ring_slot(itq) * KV_BYTES), idesc_pv, t != 0);
+                umma_commit(&ring_empty[ring_slot(itq)]);
                 umma_commit(&pds_done[t & 1]);
             }
         }
