@@ -18,18 +18,32 @@ What is mirrored (reference file:line):
     make_mm_config / make_data_module         :671-717
 The webdataset / GCS reader (:466-520) is replaced by `TarShardDataset`, a plain tarfile reader of the same
 on-disk format (`<key>.audio_encoding.pyd` pickle + `<key>.json`), sharded by rank like wds.split_by_node.
+
+On-disk formats either side of the path, same names and behaviour:
+    read_jsonl_data                           :49-55
+    preprocess_multimodal / preprocess_for_lm :112-178 (the list-of-sources forms)
+    assert_hf_src_format / _to_conversation_hf :343-427 (batched dict-of-lists -> one QA pair per element)
+    maybe_add_gcs_prefix / repeat_shards      :430-463 (task_sample_probs, 1024 x len(urls) resampled shard list)
+    gen_from_msgpack_shards                   :599-615 (a shard is ONE msgpack list of examples)
+    hf_preprocess_encodings                   :618-622
+    read_hf_dataset                           :625-668 -> `HFStyleShardDataset` (jsonl / msgpack shards without the
+                                              `datasets` dependency: split by node, batch-8 flat-map, shuffle buffer
+                                              1000, then the three per-element maps)
 """
 import copy
 import io
 import json
 import logging
+import os
 import pickle
 import random
 import tarfile
+from collections import defaultdict
 from dataclasses import dataclass
 from functools import partial
 from typing import Any, Dict, List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from llark_b200.special_tokens import (DEFAULT_AUDIO_END_TOKEN, DEFAULT_AUDIO_PATCH_TOKEN, DEFAULT_AUDIO_START_TOKEN,
@@ -251,6 +265,229 @@ def expand_url_to_file_list(url: str) -> List[str]:
         for i in range(int(a), int(b) + 1):
             out.append(part[: m.start()] + str(i).zfill(width) + part[m.end():])
     return out
+
+
+def read_jsonl_data(file) -> List[Dict[Any, Any]]:
+    """Read and parse a jsonl file line by line (m2t/data_modules.py:49-55)."""
+    logging.debug(f"reading {file}")
+    with open(file, "r") as f:
+        return [json.loads(line) for line in f]
+
+
+def preprocess_multimodal(sources: Sequence[Sequence[Dict[str, str]]], multimodal_cfg: dict,
+                          encoded_shapes: Sequence[Sequence[int]]):
+    """List-of-sources form of the <audio> expansion (m2t/data_modules.py:112-143); mutates `sources` in place."""
+    if not multimodal_cfg["is_multimodal"]:
+        return sources
+    for encoded_shape, source in zip(encoded_shapes, sources):
+        audio_token_len, audio_token_dim = encoded_shape
+        if multimodal_cfg["sep_audio_conv_front"]:
+            assert DEFAULT_AUDIO_TOKEN in source[0]["value"]
+            source[0]["value"] = source[0]["value"].replace(DEFAULT_AUDIO_TOKEN, "").strip()
+            source[0]["value"] = (DEFAULT_AUDIO_TOKEN + CONVERSATION_SEP + CONVERSATION_ROLES[0] + ": "
+                                  + source[0]["value"])
+        replace_token = DEFAULT_AUDIO_PATCH_TOKEN * audio_token_len
+        if multimodal_cfg["use_audio_start_end"]:
+            replace_token = DEFAULT_AUDIO_START_TOKEN + replace_token + DEFAULT_AUDIO_END_TOKEN
+        for sentence in source:
+            sentence["value"] = sentence["value"].replace(DEFAULT_AUDIO_TOKEN, replace_token)
+    return sources
+
+
+def preprocess_for_lm(sources: Sequence[Sequence[Dict[str, str]]], tokenizer) -> Dict:
+    """List-of-sources form of tokenise + mask (m2t/data_modules.py:146-177)."""
+    conversations = []
+    for source in sources:
+        header = DEFAULT_CONVERSATION_HEADER
+        conversations.append(sentences_to_formatted_conversation(header, source))
+    conversations_tokenized = _tokenize_fn(conversations, tokenizer)
+    input_ids = conversations_tokenized["input_ids"]
+    targets = copy.deepcopy(input_ids)
+    for target, source in zip(targets, sources):
+        tokenized_lens = _tokenize_fn([header] + [s["value"] for s in source], tokenizer)["input_ids_lens"]
+        speakers = [sentence["from"] for sentence in source]
+        _mask_targets(target, tokenized_lens, speakers)
+    return dict(input_ids=input_ids, labels=targets)
+
+
+def assert_hf_src_format(src):
+    """dict of equal-length lists, element i of the batch = src[k][i] for every k (m2t/data_modules.py:343-365)."""
+    assert isinstance(src, dict)
+    dict_keys = list(src.keys())
+    assert all(isinstance(src[k], list) for k in dict_keys), \
+        f"expected dict of lists, got: {[(k, type(src[k])) for k in dict_keys]}"
+    assert all(len(src[k]) == len(src[dict_keys[0]]) for k in dict_keys), \
+        f"expected lists of same length, got {[(k, len(src[k])) for k in dict_keys]}"
+
+
+def _to_conversation_hf(src: Dict[str, List]) -> Dict[str, List]:
+    """Unpack the (multiple) QA responses of every element of a batch into standalone QA-pair elements carrying the
+    audio encoding and its shape (m2t/data_modules.py:368-427); consumes random.uniform once per QA pair."""
+    output_dict = defaultdict(list)
+    assert_hf_src_format(src)
+    batch_size = len(src["__key__"])
+    for i in range(batch_size):
+        elem_json = src["json"][i]
+        elem_id = src["__key__"][i]
+        elem_audio_encoding = src["audio_encoding"][i]
+        elem_audio_encoding_shape = src["audio_encoding_shape"][i]
+        if not elem_json.get("response"):
+            logging.warning(f"no response for {src['__key__'][i]}; skipping")
+            continue
+        if not isinstance(elem_json["response"], list):
+            logging.warning(f"invalid response for {src['__key__'][i]} (could be empty); skipping")
+            continue
+        output_json = {k: elem_json[k] for k in elem_json.keys() if k != "response"}
+        for response in elem_json["response"]:
+            question, answer = (response["question"], response["answer"])
+            audio_first = random.uniform(0.0, 1.0) > 0.5
+            if audio_first:
+                prompt_text = "\n".join(("<audio>", question))
+            else:
+                prompt_text = "\n".join((question, "<audio>"))
+            output = {"audio_encoding": elem_audio_encoding, "audio_encoding_shape": elem_audio_encoding_shape,
+                      "__key__": elem_id, "id": elem_id, "json": output_json,
+                      "conversations": [{"from": "human", "value": prompt_text}, {"from": "gpt", "value": answer}]}
+            for k, v in output.items():
+                output_dict[k].append(v)
+    return output_dict
+
+
+def maybe_add_gcs_prefix(f: str) -> str:
+    """m2t/data_modules.py:430-433 (the string transformation only; GCS I/O itself is out of scope)."""
+    if f.startswith("gs://"):
+        return f"pipe:gsutil cat {f}"
+    return f
+
+
+def repeat_shards(urls: List[str], task_sample_probs: Optional[Dict[str, float]] = None):
+    """1024 x len(urls) shards resampled with replacement (np.random.choice), optionally weighted by the first
+    task_sample_probs key contained in the shard name (m2t/data_modules.py:441-463)."""
+    if task_sample_probs is not None:
+        logging.warning(f"applying task probs {task_sample_probs}")
+
+        def _shard_prob(shard) -> float:
+            for k, prob in task_sample_probs.items():
+                if k in shard:
+                    return prob
+            raise ValueError(f"probability for shard {shard} not defined in probs {task_sample_probs}")
+
+        probs = [_shard_prob(s) for s in urls]
+        probs = np.array(probs) / sum(probs)
+    else:
+        probs = None
+    _REPEATS = 1024 * len(urls)
+    return np.random.choice(urls, size=_REPEATS, replace=True, p=probs).tolist()
+
+
+def _msgpack_decode(data: bytes):
+    try:
+        import msgspec
+
+        return msgspec.msgpack.decode(data)
+    except ImportError:
+        import msgpack
+
+        return msgpack.unpackb(data, raw=False)
+
+
+def gen_from_msgpack_shards(shards):
+    """Yield the examples of msgpack shards; a shard is ONE msgpack-encoded list (m2t/data_modules.py:599-615).
+    Missing / undecodable shards are skipped with a warning."""
+    for shard in shards:
+        if (not os.path.exists(shard)) and ("gs://" not in shard):
+            logging.warning(f"skipping nonexistent shard {shard}")
+            continue
+        try:
+            with open(shard, "rb") as f:
+                decoded = _msgpack_decode(f.read())
+        except Exception as e:  # noqa: BLE001
+            logging.warning(f"error decoding data from shard {shard}: {e}; skipping.")
+            continue
+        assert isinstance(decoded, list), f"expected list after decoding {shard}; got {type(decoded)}"
+        for sample in decoded:
+            yield sample
+
+
+def hf_preprocess_encodings(src: Dict[str, Any]) -> Dict[str, Any]:
+    """Reshape the flat encoding in place (m2t/data_modules.py:618-622)."""
+    src["audio_encoding"] = preprocess_encodings(src["audio_encoding"], src["audio_encoding_shape"])
+    return src
+
+
+_SHUFFLE_BUFFER_SIZE = 1000  # the HF IterableDataset default the reference relies on (:523)
+
+
+class HFStyleShardDataset(torch.utils.data.IterableDataset):
+    """read_hf_dataset (m2t/data_modules.py:625-668) without the `datasets` package: jsonl / json or msgpack shards ->
+    examples split by node (example i goes to rank i % world, what split_dataset_by_node does for a non-sharded
+    stream) -> `_to_conversation_hf` over batches of 8 (flat-map) -> shuffle buffer of 1000 -> the <audio> expansion,
+    tokenise + mask, encoding reshape. Element dicts carry the keys the collator reads."""
+
+    def __init__(self, urls, multimodal_cfg, tokenizer, is_train, rank=0, world=1, seed=0, batch_size=8,
+                 shuffle_buffer=_SHUFFLE_BUFFER_SIZE):
+        self.urls = repeat_shards(list(urls)) if is_train else list(urls)
+        self.cfg, self.tokenizer = multimodal_cfg, tokenizer
+        self.rank, self.world, self.seed = rank, world, seed
+        self.batch_size, self.shuffle_buffer = batch_size, shuffle_buffer
+
+    def _examples(self):
+        if self.urls[0].endswith(".jsonl") or self.urls[0].endswith(".json"):
+            for u in self.urls:
+                yield from read_jsonl_data(u)
+        elif self.urls[0].endswith(".msgpack"):
+            yield from gen_from_msgpack_shards(self.urls)
+        else:
+            raise ValueError(f"unsupported shard type {self.urls[0]} (expected .jsonl, .json or .msgpack)")
+
+    def _flat(self):
+        batch = defaultdict(list)
+        n = 0
+        for i, ex in enumerate(self._examples()):
+            if i % self.world != self.rank:
+                continue
+            for k, v in ex.items():
+                batch[k].append(v)
+            n += 1
+            if n == self.batch_size:
+                out = _to_conversation_hf(dict(batch))
+                for j in range(len(out.get("__key__", []))):
+                    yield {k: v[j] for k, v in out.items()}
+                batch, n = defaultdict(list), 0
+        if n:
+            out = _to_conversation_hf(dict(batch))
+            for j in range(len(out.get("__key__", []))):
+                yield {k: v[j] for k, v in out.items()}
+
+    def __iter__(self):
+        rng = random.Random(self.seed)
+        mm = partial(preprocess_multimodal_mappable, multimodal_cfg=self.cfg)
+        lm = partial(preprocess_for_lm_mappable, tokenizer=self.tokenizer)
+
+        def finish(e):
+            # datasets.map(batched=False) MERGES the returned dict into the example, which is why the reference can
+            # still find `audio_encoding_shape` after preprocess_for_lm_mappable dropped it
+            e = {**e, **mm(e)}
+            e = {**e, **lm(e)}
+            return hf_preprocess_encodings(e)
+
+        buf = []
+        for e in self._flat():
+            if len(buf) < self.shuffle_buffer:
+                buf.append(e)
+                continue
+            k = rng.randrange(self.shuffle_buffer)
+            yield finish(buf[k])
+            buf[k] = e
+        rng.shuffle(buf)
+        for e in buf:
+            yield finish(e)
+
+
+def read_hf_dataset(url: str, multimodal_cfg: Dict[str, Any], tokenizer, is_train: bool, rsample_frac=None):
+    """m2t/data_modules.py:625-668: RANK / WORLD_SIZE come from the environment as in the reference."""
+    return HFStyleShardDataset(expand_url_to_file_list(url), multimodal_cfg, tokenizer, is_train,
+                               rank=int(os.environ["RANK"]), world=int(os.environ["WORLD_SIZE"]))
 
 
 def make_mm_config(data_args):
