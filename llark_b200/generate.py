@@ -1,0 +1,69 @@
+"""Generation plumbing of the inference path: mirror of m2t/generate.py plus the decoding loop
+behind `WrappedLlamav2ForCausalLM.generate`.
+
+    KeywordsStoppingCriteria    m2t/generate.py:18-44 (same constructor, same __call__ contract)
+    greedy_generate             the greedy branch of transformers' GenerationMixin.generate as m2t/infer.py:99-152 uses it
+                                (batch of one prompt, stopping criteria, eos), run WITHOUT a KV cache: every step is one
+                                full forward of the fused engine over the sequence so far. The KV-cache decode kernels are
+                                the remaining part of this row; results are identical, cost is O(n^2).
+"""
+from typing import Callable, Optional, Sequence
+
+import torch
+import transformers
+
+
+class KeywordsStoppingCriteria(transformers.StoppingCriteria):
+    def __init__(self, keywords, tokenizer, input_ids):
+        self.keywords = keywords
+        self.keyword_ids = [tokenizer(keyword).input_ids for keyword in keywords]
+        # only keywords that tokenise to exactly ONE id take the fast path (with a BOS-prepending tokenizer: none)
+        self.keyword_ids = [keyword_id[0] for keyword_id in self.keyword_ids
+                            if isinstance(keyword_id, list) and len(keyword_id) == 1]
+        self.tokenizer = tokenizer
+        self.start_len = None
+        self.input_ids = input_ids
+
+    def __call__(self, output_ids: torch.LongTensor, scores: torch.FloatTensor, **kwargs) -> bool:
+        if self.start_len is None:
+            self.start_len = self.input_ids.shape[1]
+        for keyword_id in self.keyword_ids:
+            if output_ids[0, -1] == keyword_id:
+                return True
+        outputs = self.tokenizer.batch_decode(output_ids[:, self.start_len:], skip_special_tokens=True)[0]
+        for keyword in self.keywords:
+            if keyword in outputs:
+                return True
+        return False
+
+
+@torch.no_grad()
+def greedy_generate(step_logits: Callable[[torch.Tensor], torch.Tensor], input_ids: torch.Tensor,
+                    max_new_tokens: int, eos_token_id: Optional[Sequence[int]] = None,
+                    stopping_criteria: Sequence[Callable] = (), pad_token_id: Optional[int] = None) -> torch.Tensor:
+    """Greedy decoding as GenerationMixin does it for a decoder-only model: `step_logits(ids)` returns the logits of
+    the LAST position for every row of `ids` [B, t]; argmax is appended; a row is finished when it emitted an eos id;
+    finished rows are padded with pad_token_id; the loop ends when every row is finished, a stopping criterion fires
+    (evaluated on the extended sequence, scores = the step's logits) or max_new_tokens is reached. Returns the full
+    sequences [B, prompt + new]."""
+    if input_ids.dim() != 2:
+        raise ValueError("input_ids must be [batch, seq]")
+    eos = set(int(e) for e in (eos_token_id or ()))
+    if eos and pad_token_id is None:
+        pad_token_id = min(eos)  # transformers: "Setting pad_token_id to eos_token_id"
+    unfinished = torch.ones(input_ids.shape[0], dtype=torch.bool, device=input_ids.device)
+    for _ in range(max(int(max_new_tokens), 0)):
+        logits = step_logits(input_ids)
+        next_tokens = logits.float().argmax(dim=-1)
+        if eos:
+            next_tokens = torch.where(unfinished, next_tokens, torch.full_like(next_tokens, pad_token_id))
+        input_ids = torch.cat([input_ids, next_tokens[:, None].to(input_ids.dtype)], dim=1)
+        if eos:
+            hit = torch.zeros_like(unfinished)
+            for e in eos:
+                hit |= next_tokens == e
+            unfinished = unfinished & ~hit
+        stop = any(bool(torch.as_tensor(c(input_ids, logits)).all()) for c in stopping_criteria)
+        if stop or not bool(unfinished.any()):
+            break
+    return input_ids

@@ -114,10 +114,12 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         audio_encodings=None,
         **kwargs,
     ):
-        """Same signature and return value as m2t/models/llamav2.py:259-337. Training/scoring path only:
-        KV-cache decoding (past_key_values / use_cache=True) is the "next" row of SURVEY §8(f)."""
+        """Same signature and return value as m2t/models/llamav2.py:259-337. Training / scoring / cache-less
+        generation (`generate` below). KV-cache decoding (past_key_values / use_cache=True) is the remaining part of
+        SURVEY §8(f) row 2."""
         if past_key_values is not None or use_cache:
-            raise NotImplementedError("KV-cache decoding is not part of the round-1 hot path (SURVEY §8(f).2)")
+            raise NotImplementedError("KV-cache decoding kernels are not built yet (SURVEY §8(f).2); "
+                                      "WrappedLlamav2ForCausalLM.generate decodes without a cache")
         if position_ids is not None:
             S = input_ids.shape[1]
             if not torch.equal(position_ids.reshape(-1, S)[0].cpu(), torch.arange(S)):
@@ -150,6 +152,49 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
                              "use_cache": kwargs.get("use_cache", True),
                              "audio_encodings": kwargs.get("audio_encodings", None)})
         return model_inputs
+
+    @torch.no_grad()
+    def generate(self, inputs=None, input_ids=None, audio_encodings=None, stopping_criteria=None, max_new_tokens=None,
+                 max_length=None, do_sample=None, num_beams=None, eos_token_id=None, pad_token_id=None, **kwargs):
+        """`model.generate(input_ids=, audio_encodings=, stopping_criteria=[...], max_new_tokens=...)` as called at
+        m2t/infer.py:146-152 (and scripts/inference/*.py): greedy decoding of one prompt, returns the full sequences
+        [B, prompt + new] like GenerationMixin. Sampling / beam search are not built. No KV cache yet: each step is a
+        full forward over the sequence so far (llark_b200/generate.py); extra keyword arguments the reference passes
+        along (`labels`, `example_id`, `id`) are ignored as transformers ignores / rejects them."""
+        from llark_b200.generate import greedy_generate
+
+        if input_ids is None:
+            input_ids = inputs
+        if input_ids is None:
+            raise ValueError("generate needs input_ids")
+        if do_sample or (num_beams not in (None, 1)):
+            raise NotImplementedError("llark_b200 generates greedily (do_sample=False, num_beams=1)")
+        gc = getattr(self, "generation_config", None)
+        if max_new_tokens is None:
+            total = max_length if max_length is not None else (getattr(gc, "max_length", None) or 20)
+            max_new_tokens = max(int(total) - input_ids.shape[1], 0)
+        if eos_token_id is None:
+            eos_token_id = getattr(gc, "eos_token_id", None)
+            if eos_token_id is None:
+                eos_token_id = getattr(self.config, "eos_token_id", None)
+        if isinstance(eos_token_id, int):
+            eos_token_id = [eos_token_id]
+        if pad_token_id is None:
+            pad_token_id = getattr(gc, "pad_token_id", None)
+        if pad_token_id is None:
+            pad_token_id = getattr(self.config, "pad_token_id", None)
+        was_training = self.training
+        self.eval()
+
+        def step_logits(ids):
+            out = self.forward(input_ids=ids, audio_encodings=audio_encodings, use_cache=False, return_dict=True)
+            return out.logits[:, -1, :]
+
+        try:
+            return greedy_generate(step_logits, input_ids, max_new_tokens, eos_token_id=eos_token_id,
+                                   stopping_criteria=list(stopping_criteria or []), pad_token_id=pad_token_id)
+        finally:
+            self.train(was_training)
 
     def initialize_audio_tokenizer(self, mm_use_audio_start_end, tokenizer, device, tune_mm_mlp_adapter=False,
                                    pretrain_mm_mlp_adapter=None):

@@ -17,6 +17,7 @@ class SynthTokenizer:
         self.model_max_length = model_max_length
         self.bos_token_id, self.eos_token_id, self.unk_token_id = 1, 2, 0
         self.special = {}
+        self.pieces = {}
         self.pad_token_id = None
         self.padding_side = "right"
 
@@ -56,8 +57,27 @@ class SynthTokenizer:
                 ids.append(self.special[part])
                 continue
             for piece in re.findall(r"\w+|[^\w\s]|\s+", part):
-                ids.append(3 + zlib.crc32(piece.encode("utf-8")) % (self.base_vocab - 3))
+                tid = 3 + zlib.crc32(piece.encode("utf-8")) % (self.base_vocab - 3)
+                self.pieces.setdefault(tid, piece)  # reverse vocabulary for decode(): first piece seen per id
+                ids.append(tid)
         return ids
+
+    def decode(self, ids, skip_special_tokens=False):
+        """Inverse of _encode for ids this instance has produced (unknown ids render as <id>); BOS/EOS/UNK and the
+        added special tokens are dropped when skip_special_tokens is set, as the HF tokenizers do."""
+        rev = {v: k for k, v in self.special.items()}
+        out = []
+        for t in (ids.tolist() if hasattr(ids, "tolist") else list(ids)):
+            t = int(t)
+            if t in (self.bos_token_id, self.eos_token_id, self.unk_token_id) or t in rev:
+                if not skip_special_tokens:
+                    out.append(rev.get(t, {self.bos_token_id: "<s>", self.eos_token_id: "</s>"}.get(t, "<unk>")))
+                continue
+            out.append(self.pieces.get(t, f"<{t}>"))
+        return "".join(out)
+
+    def batch_decode(self, batch, skip_special_tokens=False):
+        return [self.decode(row, skip_special_tokens=skip_special_tokens) for row in batch]
 
     def __call__(self, text, return_tensors=None, padding=None, max_length=None, truncation=False,
                  add_special_tokens=True):

@@ -200,3 +200,46 @@ def test_optimizer_step_then_backward_overwrites_stale_grads(gold):
     for n, p in model.named_parameters():
         if p.grad is not None:
             assert _rel(p.grad.float(), 2 * g_a[n]) < 2e-2, n
+
+
+def test_generate_greedy_decoding_without_cache():
+    """WrappedLlamav2ForCausalLM.generate (m2t/infer.py:146-152 call shape): cache-less greedy decoding on the CUDA
+    engine. Every generated token must be the argmax of a teacher-forced forward up to bf16 noise, the sequence must
+    equal the reference's GenerationMixin.generate (tests/golden/generation_ref.pt, fp32) up to the first step whose
+    fp32 top-2 margin is below 0.05, and eos / stopping criteria / max_length must cut it where the reference's do."""
+    from oracle import llama_oracle as lo
+    from oracle.make_golden_generation import StopOnToken, gen_inputs
+
+    gold_gen = torch.load(os.path.join(GOLD, "generation_ref.pt"), weights_only=False)["generate"]
+    cfg, params, ids, enc = gen_inputs()
+    model = build_model(cfg, params)
+    ids_c, enc_c = ids.cuda(), enc.cuda()
+    P = ids.shape[1]
+    seq = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_new_tokens=8, labels=None, example_id="x")
+    assert seq.shape == (1, P + 8) and torch.equal(seq[:, :P], ids_c)
+    with torch.no_grad():
+        logits = model(input_ids=seq[:, :-1], audio_encodings=enc_c).logits.float()[0]
+    for t in range(P, P + 8):
+        row = logits[t - 1]
+        assert row[seq[0, t]] >= row.max() - 3e-2 * row.abs().max(), t
+    ref = gold_gen["sequences"]["plain"][0]
+    ref_logits = lo.forward(params, cfg, ref[None, :-1], None, None, enc)[1][0]
+    for t in range(P, P + 8):
+        top = ref_logits[t - 1].topk(2).values
+        if (top[0] - top[1]).item() < 0.05:
+            break
+        assert seq[0, t].item() == ref[t].item(), t
+    new = seq[0, P:].tolist()
+    # eos: emitted, then generation stops
+    first = new.index(new[2])
+    out = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_new_tokens=8, eos_token_id=new[2])
+    assert out[0].tolist() == seq[0, : P + first + 1].tolist()
+    # stopping criterion (the KeywordsStoppingCriteria calling convention)
+    first = new.index(new[3])
+    out = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_new_tokens=8, stopping_criteria=[StopOnToken(new[3])])
+    assert out[0].tolist() == seq[0, : P + first + 1].tolist()
+    # max_length counts the prompt
+    out = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_length=P + 3)
+    assert out[0].tolist() == seq[0, : P + 3].tolist()
+    with pytest.raises(NotImplementedError):
+        model.generate(input_ids=ids_c, audio_encodings=enc_c, do_sample=True)
