@@ -118,6 +118,11 @@ int llark_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows
  * Backward writes dq|dk|dv into dqkv (same packing). workspace: llark_attn_bwd_workspace bytes. */
 int llark_attn_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
                    int head_dim, float scale, cudaStream_t stream);
+/* Single-token decode step against a KV cache (transformers' cached LlamaAttention behind m2t/infer.py's
+ * model.generate): q [B, n_heads*128] (RoPE applied), k_cache / v_cache [B, s_max, n_heads*128] bf16, lens int32 [B] =
+ * valid cached positions per row including the new token (<= s_max <= 4096), out [B, n_heads*128]. */
+int llark_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* lens, void* out, int B,
+                      int s_max, int n_heads, int head_dim, float scale, cudaStream_t stream);
 long long llark_attn_bwd_workspace(int B, int S, int n_heads);
 int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout, const float* lse,
                    void* dqkv, int B, int S, int n_heads, int head_dim, float scale, void* workspace,

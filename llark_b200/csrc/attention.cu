@@ -246,6 +246,69 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const unsigned char* __re
     }
 }
 
+// =============================================================================================== decode (KV cache)
+// One new query token per sequence against the cached keys/values of the positions before it (and itself): the
+// single-token step of m2t/infer.py's model.generate (transformers' cached LlamaAttention, reached from
+// m2t/models/llamav2.py:224 with past_key_values). HBM-bound: per (batch row, head) it streams len x 128 bf16 of K
+// and of V once. grid (n_heads, B), 128 threads:
+//   phase 1: thread j (stride 128) scores key j: dot(q, K[j]) with q in shared memory, K rows read as 16 B vectors;
+//   phase 2: block max / sum of exp over the scores kept in shared memory (len <= 4096);
+//   phase 3: thread d owns output channel d: sum_j p[j] * V[j][d] (a warp reads 64 contiguous bytes of a V row).
+// q: [B, n_heads*128] (RoPE applied); k_cache / v_cache: [B, s_max, n_heads*128]; lens[b] = number of valid cached
+// positions of row b INCLUDING the new token; out [B, n_heads*128].
+constexpr int DEC_MAX_LEN = 4096;
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                   const __nv_bfloat16* __restrict__ vc, const int* __restrict__ lens, __nv_bfloat16* __restrict__ out,
+                   int s_max, int NH, float scale_log2) {
+    __shared__ float sq[HD];
+    __shared__ float sp[DEC_MAX_LEN];
+    __shared__ float red[4];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int len = min(lens[b], s_max);
+    const long long row = (long long)NH * HD;
+    const __nv_bfloat16* kb = kc + (long long)b * s_max * row + (long long)h * HD;
+    const __nv_bfloat16* vb = vc + (long long)b * s_max * row + (long long)h * HD;
+    sq[threadIdx.x] = __bfloat162float(q[(long long)b * row + (long long)h * HD + threadIdx.x]);
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < len; j += 128) {
+        const __nv_bfloat16* kr = kb + (long long)j * row;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; c += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(kr + c);
+            const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            dot = fmaf(sq[c], a.x, dot); dot = fmaf(sq[c + 1], a.y, dot);
+            dot = fmaf(sq[c + 2], b2.x, dot); dot = fmaf(sq[c + 3], b2.y, dot);
+            dot = fmaf(sq[c + 4], c2.x, dot); dot = fmaf(sq[c + 5], c2.y, dot);
+            dot = fmaf(sq[c + 6], d.x, dot); dot = fmaf(sq[c + 7], d.y, dot);
+        }
+        dot *= scale_log2;
+        sp[j] = dot;
+        mx = fmaxf(mx, dot);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < len; j += 128) {
+        const float p = exp2f(sp[j] - mx);
+        sp[j] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = red[0] + red[1] + red[2] + red[3];
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    float acc = 0.f;
+    for (int j = 0; j < len; ++j) acc = fmaf(sp[j], __bfloat162float(vb[(long long)j * row + threadIdx.x]), acc);
+    out[(long long)b * row + (long long)h * HD + threadIdx.x] = __float2bfloat16_rn(acc * inv);
+}
+
 // =============================================================================================== backward
 // Dsum[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (b,s,h).
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
@@ -565,6 +628,16 @@ static inline int check_launch2() {
 }  // namespace llark
 
 using namespace llark;
+
+extern "C" int llark_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* lens, void* out,
+                                 int B, int s_max, int n_heads, int head_dim, float scale, cudaStream_t st) {
+    if (head_dim != HD || B <= 0 || s_max <= 0 || s_max > DEC_MAX_LEN || n_heads <= 0 || !lens) return LLARK_EINVAL;
+    dim3 grid(n_heads, B);
+    attn_decode_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k_cache,
+                                             (const __nv_bfloat16*)v_cache, lens, (__nv_bfloat16*)out, s_max, n_heads,
+                                             scale * LOG2E);
+    return check_launch2();
+}
 
 extern "C" int llark_attn_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S,
                               int n_heads, int head_dim, float scale, cudaStream_t st) {

@@ -116,6 +116,25 @@ class FlatBuckets:
         self.consumed = False
 
 
+class KVCache:
+    """Per-layer key / value store of the generation path (what transformers hands around as `past_key_values`):
+    k[l], v[l] are bf16 [B, s_max, H] in the token-major layout of the packed qkv buffer (keys post-RoPE); `length` is
+    the number of cached positions, the same for every row (the reference decodes one prompt at a time)."""
+
+    def __init__(self, n_layers, B, s_max, H, device):
+        self.k = [torch.empty((B, s_max, H), device=device, dtype=BF16) for _ in range(n_layers)]
+        self.v = [torch.empty((B, s_max, H), device=device, dtype=BF16) for _ in range(n_layers)]
+        self.B, self.s_max, self.H = B, s_max, H
+        self.length = 0
+        self.lens = torch.zeros(B, device=device, dtype=torch.int32)
+
+    def __len__(self):  # `if past_key_values:` of prepare_inputs_for_generation (m2t/models/llamav2.py:346)
+        return self.length
+
+    def get_seq_length(self, layer_idx=0):
+        return self.length
+
+
 class _StepFn(torch.autograd.Function):
     """Autograd anchor: forward runs the whole CUDA forward, backward the whole manual CUDA backward, which writes
     the flat gradient bucket and attaches `.grad` views (so no per-parameter autograd accumulation kernels)."""
@@ -197,7 +216,7 @@ class LlamaEngine:
         return self._forward(batch, need_grad=False)
 
     # ------------------------------------------------------------------------------------------ forward
-    def _forward(self, batch, need_grad):
+    def _forward(self, batch, need_grad, kv_sink=None):
         cfg, flat = self.cfg, self.flat
         ids = batch["input_ids"]
         if ids.dtype != torch.int64:
@@ -279,6 +298,10 @@ class LlamaEngine:
                 qkv = ops.gemm(xn1, Wqkv)
                 ops.rope_(qkv, cos, sin, S, NH, D)
                 n0 += 1
+            if kv_sink is not None:  # prefill of the generation path: keep the (post-RoPE) keys and the values
+                q3 = qkv.view(B, S, 3, H)
+                kv_sink.k[l][:, :S].copy_(q3[:, :, 1])
+                kv_sink.v[l][:, :S].copy_(q3[:, :, 2])
             attn, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
             x_mid = ops.gemm(attn, Wo, residual=x)
             rstd2 = torch.empty(M, device=dev, dtype=torch.float32)
@@ -316,6 +339,75 @@ class LlamaEngine:
         self._saved = saved if need_grad else None
         self.launches = n0
         return loss, logits
+
+    # ------------------------------------------------------------------------------------------ generation (KV cache)
+    # STAGED: compiled and unit-structured in round 1 but not yet run on a B200 (LLARK_KV_CACHE=1 enables it;
+    # tests/test_model_gpu.py::test_generate_with_kv_cache_matches_cacheless is gated on the same variable).
+    def new_cache(self, B, s_max, device):
+        cfg = self.cfg
+        return KVCache(cfg.num_hidden_layers, B, s_max, cfg.hidden_size, device)
+
+    @torch.no_grad()
+    def prefill(self, input_ids, audio_encodings, cache):
+        """Full forward over the prompt that also fills `cache`; returns logits [B, S, V]."""
+        self.ensure_packed()
+        B, S = input_ids.shape
+        if S > cache.s_max or B != cache.B:
+            raise ValueError("prompt does not fit the KV cache")
+        batch = dict(input_ids=input_ids, attention_mask=None, labels=None, audio_encodings=audio_encodings)
+        _, logits = self._forward(batch, need_grad=False, kv_sink=cache)
+        cache.length = S
+        cache.lens.fill_(S)
+        return logits
+
+    @torch.no_grad()
+    def decode_step(self, last_ids, cache):
+        """One token per row: last_ids int64 [B, 1] at position cache.length -> logits [B, 1, V]; appends to the cache."""
+        cfg, flat = self.cfg, self.ensure_packed()
+        dev = last_ids.device
+        B = last_ids.shape[0]
+        H, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        NH = cfg.num_attention_heads
+        D = H // NH
+        V = self.lm.lm_head.weight.shape[0]
+        eps = cfg.rms_norm_eps
+        t = cache.length
+        if t >= cache.s_max:
+            raise ValueError("KV cache is full")
+        ids = last_ids.to(torch.int64).contiguous()
+        table = flat.pview("model.embed_tokens.weight", (V, H))
+        x = torch.empty((B, H), device=dev, dtype=BF16)
+        ops.embed_splice_fwd(ids, table, None, None, None, None, x.view(B, 1, H))
+        cos, sin = self._tables(cache.s_max, dev)
+        cos_t, sin_t = cos[t:], sin[t:]  # row 0 of these views is position t: with S = 1 every row reads it
+        cache.lens.fill_(t + 1)
+        rstd = torch.empty(B, device=dev, dtype=torch.float32)
+        for l in range(L):
+            pfx = f"model.layers.{l}."
+            Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
+            Wo = flat.pview(pfx + "self_attn.o_proj.weight", (H, H))
+            Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
+            Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
+            xn1 = ops.rmsnorm_fwd(x, flat.pview(pfx + "input_layernorm.weight"), eps, rstd=rstd)
+            if self.fuse_epilogues and D == 128:
+                qkv = ops.gemm(xn1, Wqkv, rope=(cos_t, sin_t, 1, 2 * H))
+            else:
+                qkv = ops.gemm(xn1, Wqkv)
+                ops.rope_(qkv, cos_t, sin_t, 1, NH, D)
+            cache.k[l][:, t].copy_(qkv[:, H:2 * H])
+            cache.v[l][:, t].copy_(qkv[:, 2 * H:])
+            attn = ops.attn_decode(qkv[:, :H].contiguous(), cache.k[l], cache.v[l], cache.lens, NH, D)
+            x_mid = ops.gemm(attn, Wo, residual=x)
+            xn2 = ops.rmsnorm_fwd(x_mid, flat.pview(pfx + "post_attention_layernorm.weight"), eps, rstd=rstd)
+            gu = ops.gemm(xn2, Wgu)
+            act = ops.swiglu_fwd(gu)
+            x = ops.gemm(act, Wd, residual=x_mid)
+        hn = ops.rmsnorm_fwd(x, flat.pview("model.norm.weight"), eps, rstd=rstd)
+        ldv = (V + 63) // 64 * 64
+        logits_buf = torch.empty((B, ldv), device=dev, dtype=BF16)
+        ops.gemm(hn, flat.pview("lm_head.weight", (V, H)), out=logits_buf, N=V)
+        cache.length = t + 1
+        return logits_buf.view(B, 1, ldv)[:, :, :V]
 
     # ------------------------------------------------------------------------------------------ backward
     def _backward(self, dloss):

@@ -13,6 +13,7 @@ The modules are ordinary HF `nn.Module`s (they only hold the parameters, re-poin
 bucket); `forward` never calls them.
 """
 import logging
+import os
 from typing import List, Optional
 
 import torch
@@ -118,8 +119,12 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         generation (`generate` below). KV-cache decoding (past_key_values / use_cache=True) is the remaining part of
         SURVEY §8(f) row 2."""
         if past_key_values is not None or use_cache:
-            raise NotImplementedError("KV-cache decoding kernels are not built yet (SURVEY §8(f).2); "
-                                      "WrappedLlamav2ForCausalLM.generate decodes without a cache")
+            if os.environ.get("LLARK_KV_CACHE") != "1":
+                raise NotImplementedError("KV-cache decoding is staged behind LLARK_KV_CACHE=1 until it has run on a "
+                                          "B200 (SURVEY §8(f).2); WrappedLlamav2ForCausalLM.generate decodes without "
+                                          "a cache")
+            return self._forward_cached(input_ids, attention_mask, past_key_values, labels, return_dict,
+                                        audio_encodings)
         if position_ids is not None:
             S = input_ids.shape[1]
             if not torch.equal(position_ids.reshape(-1, S)[0].cpu(), torch.arange(S)):
@@ -137,6 +142,31 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
             output = (logits,)
             return (loss,) + output if loss is not None else output
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=None,
+                                      attentions=None)
+
+    def _forward_cached(self, input_ids, attention_mask, past_key_values, labels, return_dict, audio_encodings):
+        """use_cache=True: the first call (no cache) is the prefill over the whole prompt, later calls feed the newest
+        token only (m2t/models/llamav2.py:346-347). Returns `past_key_values` = the engine's KVCache."""
+        if labels is not None:
+            raise NotImplementedError("labels with use_cache=True are not supported")
+        if attention_mask is not None and not bool(attention_mask.to(torch.bool).all()):
+            raise NotImplementedError("cached decoding needs unpadded prompts (the reference decodes one prompt at a time)")
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "return_dict", True)
+        cache = past_key_values
+        if cache is None or len(cache) == 0:
+            s_max = min(int(getattr(self.config, "max_position_embeddings", 4096)), 4096)
+            if cache is None:
+                cache = self._engine.new_cache(input_ids.shape[0], s_max, input_ids.device)
+            logits = self._engine.prefill(input_ids, audio_encodings, cache)
+            if self.validate == "sync" and audio_encodings is not None:
+                self._engine.check_flags()
+        else:
+            if input_ids.shape[1] != 1:
+                input_ids = input_ids[:, -1:]
+            logits = self._engine.decode_step(input_ids, cache)
+        if not return_dict:
+            return (logits, cache)
+        return CausalLMOutputWithPast(loss=None, logits=logits, past_key_values=cache, hidden_states=None,
                                       attentions=None)
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
@@ -186,7 +216,14 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         was_training = self.training
         self.eval()
 
+        state = {"cache": None}
+
         def step_logits(ids):
+            if os.environ.get("LLARK_KV_CACHE") == "1":  # staged: prefill once, then one token per step
+                out = self.forward(input_ids=ids, audio_encodings=audio_encodings, past_key_values=state["cache"],
+                                   use_cache=True, return_dict=True)
+                state["cache"] = out.past_key_values
+                return out.logits[:, -1, :]
             out = self.forward(input_ids=ids, audio_encodings=audio_encodings, use_cache=False, return_dict=True)
             return out.logits[:, -1, :]
 

@@ -179,6 +179,15 @@ def attn_fwd(qkv, key_mask, B, S, n_heads, head_dim, out=None, lse=None):
     return out, lse
 
 
+def attn_decode(q, k_cache, v_cache, lens, n_heads, head_dim, out=None):
+    """One query token per row against the KV cache: q [B, H], caches [B, s_max, H], lens int32 [B] -> out [B, H]."""
+    B, s_max = k_cache.shape[0], k_cache.shape[1]
+    out = out if out is not None else torch.empty((B, n_heads * head_dim), device=q.device, dtype=BF16)
+    check(lib().llark_attn_decode(_p(q), _p(k_cache), _p(v_cache), _p(lens), _p(out), B, s_max, n_heads, head_dim,
+                                  1.0 / math.sqrt(head_dim), _stream()), "attn_decode")
+    return out
+
+
 def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None):
     dqkv = dqkv if dqkv is not None else torch.empty_like(qkv)
     need = lib().llark_attn_bwd_workspace(B, S, n_heads)

@@ -417,3 +417,25 @@ def test_cast_and_colsum():
     out = torch.zeros(4096, device="cuda", dtype=BF16)
     ops.colsum(xb, out)
     assert _rel(out, xb.float().sum(0)) < 4e-3
+
+
+@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
+                    reason="staged kernel that has not run on a B200 yet (set LLARK_STAGED=1)")
+@pytest.mark.parametrize("B,s_max,lens,NH", [(1, 64, [17], 2), (3, 300, [1, 300, 129], 4)])
+def test_attention_decode_step(B, s_max, lens, NH):
+    ops = _ops()
+    torch.manual_seed(31)
+    D = 128
+    q = (torch.randn(B, NH * D, device="cuda") * 0.8).to(BF16)
+    kc = (torch.randn(B, s_max, NH * D, device="cuda") * 0.8).to(BF16)
+    vc = (torch.randn(B, s_max, NH * D, device="cuda") * 0.8).to(BF16)
+    lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    out = ops.attn_decode(q, kc, vc, lens_t, NH, D)
+    for b in range(B):
+        n = lens[b]
+        qf = q[b].float().view(NH, D)
+        kf = kc[b, :n].float().view(n, NH, D).permute(1, 0, 2)
+        vf = vc[b, :n].float().view(n, NH, D).permute(1, 0, 2)
+        p = torch.softmax((kf @ qf[:, :, None]).squeeze(-1) / math.sqrt(D), dim=-1)  # [NH, n]
+        ref = (p[:, None, :] @ vf).squeeze(1).reshape(-1)
+        assert _rel(out[b], ref) < 6e-3

@@ -243,3 +243,34 @@ def test_generate_greedy_decoding_without_cache():
     assert out[0].tolist() == seq[0, : P + 3].tolist()
     with pytest.raises(NotImplementedError):
         model.generate(input_ids=ids_c, audio_encodings=enc_c, do_sample=True)
+
+
+STAGED = pytest.mark.skipif(os.environ.get("LLARK_STAGED") != "1",
+                            reason="staged code path that has not run on a B200 yet (set LLARK_STAGED=1)")
+
+
+@STAGED
+def test_generate_with_kv_cache_matches_cacheless():
+    """Prefill + single-token decode steps against the KV cache (LLARK_KV_CACHE=1) must pick the same tokens as the
+    cache-less loop and reproduce its last-position logits (bf16 noise only)."""
+    from oracle.make_golden_generation import gen_inputs
+
+    cfg, params, ids, enc = gen_inputs()
+    model = build_model(cfg, params)
+    ids_c, enc_c = ids.cuda(), enc.cuda()
+    os.environ.pop("LLARK_KV_CACHE", None)
+    ref = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_new_tokens=8)
+    with torch.no_grad():
+        full = model(input_ids=ref[:, :-1], audio_encodings=enc_c).logits.float()
+    os.environ["LLARK_KV_CACHE"] = "1"
+    try:
+        got = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_new_tokens=8)
+        out = model(input_ids=ids_c, audio_encodings=enc_c, use_cache=True)
+        cache = out.past_key_values
+        assert len(cache) == ids.shape[1] and torch.allclose(out.logits.float(), full[:, : ids.shape[1]], atol=3e-2)
+        step = model(input_ids=ref[:, ids.shape[1]: ids.shape[1] + 1], past_key_values=cache, use_cache=True)
+        assert step.logits.shape == (1, 1, cfg.vocab_size) and len(cache) == ids.shape[1] + 1
+        assert torch.allclose(step.logits.float()[0, 0], full[0, ids.shape[1]], atol=5e-2)
+    finally:
+        os.environ.pop("LLARK_KV_CACHE", None)
+    assert torch.equal(got, ref)
