@@ -140,3 +140,167 @@ def swiglu_fwd(gu, act=None):
     I = gu.shape[1] // 2
     g, u = gu[:, :I].float(), gu[:, I:].float()
     return (_round(g * torch.sigmoid(g)).float() * u).to(BF16)
+
+
+# ------------------------------------------------------------------------------------------------ backward / optimizer
+class _Lib:
+    """Workspace-size queries of the C-ABI the engine makes through ops.lib()."""
+
+    @staticmethod
+    def llark_rmsnorm_bwd_workspace(rows, H):
+        return 16
+
+    @staticmethod
+    def llark_attn_bwd_workspace(B, S, n_heads):
+        return 16
+
+    @staticmethod
+    def llark_sumsq_workspace():
+        return 16
+
+
+def lib():  # noqa: F811  (replaces the placeholder above)
+    return _Lib
+
+
+_gemm_fwd = gemm
+
+
+def gemm(a, b, **kw):  # noqa: F811
+    """Adds the SwiGLU-backward epilogue and residual-into-out accumulation to the forward stand-in."""
+    gu = kw.pop("swiglu_bwd", None)
+    if gu is None:
+        return _gemm_fwd(a, b, **kw)
+    out = kw.pop("out")
+    N = kw.get("N")
+    d = _gemm_fwd(a, b, **kw).float()[:, :N]  # d(act), rounded to bf16 as the unfused GEMM stores it
+    out.copy_(swiglu_bwd(gu, d.to(BF16)))
+    return out
+
+
+def swiglu_bwd(gu, dact, dgu=None):
+    I = gu.shape[1] // 2
+    g, u, d = gu[:, :I].float(), gu[:, I:].float(), dact.float()
+    sg = torch.sigmoid(g)
+    du = d * _round(g * sg).float()
+    dg = d * u * (sg * (1 + g * (1 - sg)))
+    return torch.cat([dg, du], dim=1).to(BF16)
+
+
+def ce_fwd(logits, ldv, V, labels, B, S, row_loss, row_lse, loss_out):
+    lg = logits.float().view(B, S, -1)[:, :, :V]
+    tgt = torch.full((B, S), -100, dtype=torch.int64)
+    tgt[:, :-1] = labels[:, 1:]
+    lse = torch.logsumexp(lg, dim=-1)
+    valid = (tgt >= 0) & (tgt < V)
+    picked = torch.gather(lg, 2, tgt.clamp(0, V - 1)[..., None]).squeeze(-1)
+    loss_rows = torch.where(valid, lse - picked, torch.zeros_like(lse))
+    row_loss.copy_(loss_rows.flatten())
+    row_lse.copy_(torch.where(valid, lse, torch.full_like(lse, float("inf"))).flatten())
+    n = valid.sum().clamp(min=1).float()
+    loss_out[0] = loss_rows.sum() / n
+    loss_out[1] = n
+
+
+def ce_bwd(logits, ldv, V, labels, B, S, row_lse, loss_out, gscale_ptr, gscale, dlogits):
+    lg = logits.float().view(B * S, -1)
+    tgt = torch.full((B, S), -100, dtype=torch.int64)
+    tgt[:, :-1] = labels[:, 1:]
+    tgt = tgt.flatten()
+    scale = (gscale_ptr[0].item() if gscale_ptr is not None else gscale) / loss_out[1].item()
+    out = torch.zeros_like(lg)
+    valid = (tgt >= 0) & (tgt < V)
+    p = torch.softmax(lg[:, :V], dim=-1)
+    p[torch.arange(B * S)[valid], tgt[valid]] -= 1.0
+    out[:, :V] = torch.where(valid[:, None], p * scale, torch.zeros_like(p))
+    dlogits.copy_(out.to(BF16).view_as(dlogits))
+
+
+def rmsnorm_bwd(x, w, dy, rstd, dres, dx, dw, accumulate_dw, workspace):
+    xf, dyf, wf = x.float(), dy.float(), w.float()
+    r = rstd.float()[:, None]
+    xhat = xf * r
+    dxhat = dyf * wf
+    g = r * (dxhat - xhat * (dxhat * xhat).mean(-1, keepdim=True))
+    if dres is not None:
+        g = g + dres.float()
+    dx.copy_(g.to(BF16))
+    if dw is not None:
+        d = (dyf * _round(xhat).float()).sum(0)
+        dw.copy_(((dw.float() if accumulate_dw else 0) + d).to(BF16))
+    return dx
+
+
+def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None):
+    x = qkv.float().clone().requires_grad_(True)
+    with torch.enable_grad():
+        q, k, v = x.view(B, S, 3, n_heads, head_dim).permute(2, 0, 3, 1, 4)
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(head_dim)
+        allow = torch.ones(S, S, dtype=torch.bool).tril()[None, None]
+        if key_mask is not None:
+            allow = allow & key_mask.view(B, 1, 1, S).bool()
+        p = torch.softmax(sc.masked_fill(~allow, float("-inf")), dim=-1)
+        o = (p @ v).permute(0, 2, 1, 3).reshape(B * S, n_heads * head_dim)
+        o.backward(dout.float())
+    return x.grad.to(BF16)
+
+
+_rope_fwd = rope_
+
+
+def rope_(qkv, cos_t, sin_t, S, n_heads, D, inverse=False):  # noqa: F811
+    if not inverse:
+        return _rope_fwd(qkv, cos_t, sin_t, S, n_heads, D)
+    rows = torch.arange(qkv.shape[0]) % S
+    W = 2 * n_heads * D
+    v = qkv[:, :W].view(qkv.shape[0], W // 128, 128)
+    c, s = cos_t[rows][:, None, :].to(BF16), sin_t[rows][:, None, :].to(BF16)
+    y = v * s
+    v.copy_((v * c) + torch.cat((y[..., 64:], -y[..., :64]), dim=-1))  # transpose of x*cos + rotate_half(x)*sin
+    return qkv
+
+
+def embed_splice_bwd(ids, dout, daudio, audio_off, frames, start_pos, dtable, vocab, detach_text):
+    B, S = ids.shape
+    for b in range(B):
+        p = int(start_pos[b]) if start_pos is not None else -1
+        F_ = int(frames[b]) if (frames is not None and p >= 0) else 0
+        for s_ in range(S):
+            if p >= 0 and p < s_ <= p + F_:
+                if daudio is not None:
+                    daudio[int(audio_off[b]) + s_ - p - 1] = dout[b, s_]
+                continue
+            if dtable is None:
+                continue
+            marker = p >= 0 and (s_ == p or s_ == p + F_ + 1)
+            if detach_text and not marker:
+                continue
+            t = int(ids[b, s_])
+            dtable[t] = (dtable[t].float() + dout[b, s_].float()).to(BF16)
+
+
+def colsum(x, out, accumulate=False):
+    out.copy_(((out.float() if accumulate else 0) + x.float().sum(0)).to(BF16))
+    return out
+
+
+def grad_sumsq(g, out, accumulate, workspace):
+    out[0] = (out[0] if accumulate else 0) + g.float().pow(2).sum()
+
+
+def adamw_step(p, g, m, v, sumsq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0,
+               zero_grad=False):
+    clip = 1.0
+    if max_norm > 0:
+        clip = min(1.0, max_norm / (math.sqrt(sumsq[0].item()) * grad_scale + 1e-6))
+    gf = _round(g.float() * (grad_scale * clip)).float()
+    pf = _round(p.float() * (1 - lr * weight_decay)).float()
+    mf = _round(torch.lerp(m.float(), gf, 1 - beta1)).float()
+    vf = _round(_round(v.float() * beta2).float() + (1 - beta2) * gf * gf).float()
+    bc1, bc2s = 1 - beta1 ** step, math.sqrt(1 - beta2 ** step)
+    den = _round(_round(_round(vf.sqrt()).float() / bc2s).float() + eps).float()
+    p.copy_(_round(pf - (lr / bc1) * mf / den))
+    m.copy_(mf.to(BF16))
+    v.copy_(vf.to(BF16))
+    if zero_grad:
+        g.zero_()

@@ -98,3 +98,51 @@ def test_generate_cacheless_and_staged_kv_cache_agree(cpu_engine, monkeypatch):
     assert agree >= 0.8, (got, ref)   # identical up to near-ties of the random-weight fixture
     with pytest.raises(ValueError):
         model._engine.prefill(torch.zeros((1, 300), dtype=torch.int64), None, cache)
+
+
+def test_engine_backward_and_optimizer_host_logic(cpu_engine, monkeypatch):
+    """Manual backward into the flat gradient bucket (views, overwrite-after-step vs accumulate, frozen lm_head, detached
+    text rows) and the fused optimizer's bookkeeping, against the oracle's autograd gradients."""
+    import cpu_ops
+    import llark_b200.optim as optim
+    from oracle import llama_oracle as lo
+
+    monkeypatch.setattr(optim, "ops", cpu_ops)
+    cfg = lo.LlamaCfg()
+    params = lo.init_params(cfg, seed=0)
+    batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=0)
+    model = _build(cfg, params)
+    for p in model.get_output_embeddings().parameters():
+        p.requires_grad = False
+    model.get_model().orig_embeds_params = [model.get_input_embeddings().weight.data.clone()]
+    opt = optim.LlarkAdamW(model, lr=1e-3)
+    out = model(**batch)
+    out.loss.backward()
+    pb = {k: v.to(BF16) for k, v in params.items()}
+    loss_o, _, grads_o = lo.forward_backward(pb, cfg, batch)
+    assert abs(out.loss.item() - loss_o.item()) < 3e-3 * loss_o.item()
+    named = dict(model.named_parameters())
+    flat = model.engine.flat
+    for name in ("model.mm_projector.weight", "model.layers.0.self_attn.q_proj.weight", "model.layers.1.mlp.down_proj.weight",
+                 "model.norm.weight", "model.layers.0.input_layernorm.weight"):
+        g = named[name].grad
+        assert g.data_ptr() == flat.gview(name).data_ptr()           # .grad IS the bucket view
+        ref = grads_o[name].float()
+        assert ((g.float() - ref).norm() / ref.norm()).item() < 6e-2, name
+    assert named["lm_head.weight"].grad is None                        # frozen (llamav2.py:412-415)
+    ge = named["model.embed_tokens.weight"].grad.float()
+    rows = ge.abs().sum(1).nonzero().flatten().tolist()
+    assert sorted(rows) == sorted({cfg.audio_start_token, cfg.audio_end_token})  # only the marker rows (Appendix D.3)
+    # accumulation: a second backward before step() adds into the bucket; after step() the next backward overwrites
+    g1 = flat.grads.float().clone()
+    model(**batch).loss.backward()
+    assert torch.allclose(flat.grads.float(), 2 * g1, rtol=2e-2, atol=1e-3)
+    opt.step()
+    assert flat.consumed
+    model(**batch).loss.backward()
+    assert not torch.allclose(flat.grads.float(), 3 * g1, rtol=1e-2, atol=1e-3)
+    l0 = out.loss.item()
+    opt.step()
+    with torch.no_grad():
+        l1 = model(**batch).loss.item()
+    assert l1 < l0
