@@ -96,7 +96,7 @@ def embed_splice_fwd(ids, table, audio, audio_off, frames, start_pos, out):
         for b in range(B):
             p = int(start_pos[b])
             if p >= 0:
-                F_ = int(frames[b])
+                F_ = min(int(frames[b]), S - p - 1)  # the kernel only writes positions inside the sequence
                 o = int(audio_off[b])
                 out[b, p + 1: p + 1 + F_] = audio[o: o + F_]
     return out
