@@ -1,33 +1,45 @@
-"""Mirror of m2t/conversation_utils.py:17-55 (example records and the prompt / response split of a token sequence)."""
-from typing import Any, Dict, List
+"""Example records and the prompt / response split of a token sequence, with the names and behaviour of
+m2t/conversation_utils.py:17-55 (pinned by tests/test_generation_cpu.py against the reference's functions)."""
+from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 
 
 def make_example(id: str, audio: str, audio_encoding: np.ndarray, audio_encoding_shape: List[int], prompt_question: str,
                  response: str) -> Dict[str, Any]:
-    return {"id": id, "audio": audio, "audio_encoding": audio_encoding, "audio_encoding_shape": audio_encoding_shape,
-            "response": [{"question": prompt_question, "answer": response}]}
+    """One dataset element in the `response: [{question, answer}]` layout the data pipeline consumes."""
+    qa = {"question": prompt_question, "answer": response}
+    return dict(id=id, audio=audio, audio_encoding=audio_encoding, audio_encoding_shape=audio_encoding_shape,
+                response=[qa])
 
 
-def subsequence_pos(ary, subary):
-    """(start, end) of the first occurrence of `subary` in `ary`; None when absent. As in the reference the last
-    possible start position is NOT examined (range(len(ary) - s)), so a match flush with the end is missed."""
+def subsequence_pos(ary, subary) -> Optional[Tuple[int, int]]:
+    """(start, end) of the first window of `ary` equal to `subary`, None when there is none. Upstream never looks at the
+    LAST window (it iterates range(len(ary) - len(subary))), so a match flush with the end is not found; kept."""
     assert isinstance(ary, list)
     assert isinstance(subary, list)
-    s = len(subary)
-    for start_idx in range(len(ary) - s):
-        if ary[start_idx: start_idx + s] == subary:
-            return start_idx, start_idx + s
+    width = len(subary)
+    n_windows = len(ary) - width  # one fewer than exist
+    start = 0
+    while start < n_windows:
+        if ary[start: start + width] == subary:
+            return start, start + width
+        start += 1
+    return None
+
+
+def _prompt_end(input_ids, end_seq) -> int:
+    found = subsequence_pos(input_ids.tolist(), end_seq)
+    # upstream unpacks the result directly, so a missing end sequence surfaces as the same TypeError
+    _, stop = found
+    return stop
 
 
 def extract_prompt_tokens(input_ids, end_seq):
-    """The input_ids of the prefix, up to and including `end_seq` (i.e. before the model's response)."""
-    _, prompt_end_idx = subsequence_pos(input_ids.tolist(), end_seq)
-    return input_ids[:prompt_end_idx]
+    """Everything up to and including `end_seq`: the prefix the model is conditioned on."""
+    return input_ids[: _prompt_end(input_ids, end_seq)]
 
 
 def extract_response_tokens(input_ids, end_seq):
-    """The input_ids of the model response (everything after `end_seq`)."""
-    _, prompt_end_idx = subsequence_pos(input_ids.tolist(), end_seq)
-    return input_ids[prompt_end_idx:]
+    """Everything after `end_seq`: the model's answer."""
+    return input_ids[_prompt_end(input_ids, end_seq):]

@@ -274,110 +274,114 @@ def read_jsonl_data(file) -> List[Dict[Any, Any]]:
         return [json.loads(line) for line in f]
 
 
+def _audio_placeholder(n_frames: int, with_markers: bool) -> str:
+    """The token string one <audio> tag expands to: n_frames patch tokens, optionally bracketed by start / end."""
+    body = DEFAULT_AUDIO_PATCH_TOKEN * n_frames
+    return DEFAULT_AUDIO_START_TOKEN + body + DEFAULT_AUDIO_END_TOKEN if with_markers else body
+
+
 def preprocess_multimodal(sources: Sequence[Sequence[Dict[str, str]]], multimodal_cfg: dict,
                           encoded_shapes: Sequence[Sequence[int]]):
-    """List-of-sources form of the <audio> expansion (m2t/data_modules.py:112-143); mutates `sources` in place."""
+    """List-of-sources form of the <audio> expansion (m2t/data_modules.py:112-143): every sentence of conversation i has
+    its <audio> tag replaced by the placeholder for encoded_shapes[i] = (frames, width); with sep_audio_conv_front the
+    tag is first moved to the front of the opening turn as "<audio>###Human: ...". Mutates and returns `sources`."""
     if not multimodal_cfg["is_multimodal"]:
         return sources
-    for encoded_shape, source in zip(encoded_shapes, sources):
-        audio_token_len, audio_token_dim = encoded_shape
+    with_markers = multimodal_cfg["use_audio_start_end"]
+    for (n_frames, _width), conversation in zip(encoded_shapes, sources):
         if multimodal_cfg["sep_audio_conv_front"]:
-            assert DEFAULT_AUDIO_TOKEN in source[0]["value"]
-            source[0]["value"] = source[0]["value"].replace(DEFAULT_AUDIO_TOKEN, "").strip()
-            source[0]["value"] = (DEFAULT_AUDIO_TOKEN + CONVERSATION_SEP + CONVERSATION_ROLES[0] + ": "
-                                  + source[0]["value"])
-        replace_token = DEFAULT_AUDIO_PATCH_TOKEN * audio_token_len
-        if multimodal_cfg["use_audio_start_end"]:
-            replace_token = DEFAULT_AUDIO_START_TOKEN + replace_token + DEFAULT_AUDIO_END_TOKEN
-        for sentence in source:
-            sentence["value"] = sentence["value"].replace(DEFAULT_AUDIO_TOKEN, replace_token)
+            opening = conversation[0]
+            assert DEFAULT_AUDIO_TOKEN in opening["value"]
+            text = opening["value"].replace(DEFAULT_AUDIO_TOKEN, "").strip()
+            opening["value"] = f"{DEFAULT_AUDIO_TOKEN}{CONVERSATION_SEP}{CONVERSATION_ROLES[0]}: {text}"
+        placeholder = _audio_placeholder(n_frames, with_markers)
+        for sentence in conversation:
+            sentence["value"] = sentence["value"].replace(DEFAULT_AUDIO_TOKEN, placeholder)
     return sources
 
 
 def preprocess_for_lm(sources: Sequence[Sequence[Dict[str, str]]], tokenizer) -> Dict:
-    """List-of-sources form of tokenise + mask (m2t/data_modules.py:146-177)."""
-    conversations = []
-    for source in sources:
-        header = DEFAULT_CONVERSATION_HEADER
-        conversations.append(sentences_to_formatted_conversation(header, source))
-    conversations_tokenized = _tokenize_fn(conversations, tokenizer)
-    input_ids = conversations_tokenized["input_ids"]
-    targets = copy.deepcopy(input_ids)
-    for target, source in zip(targets, sources):
-        tokenized_lens = _tokenize_fn([header] + [s["value"] for s in source], tokenizer)["input_ids_lens"]
-        speakers = [sentence["from"] for sentence in source]
-        _mask_targets(target, tokenized_lens, speakers)
-    return dict(input_ids=input_ids, labels=targets)
+    """List-of-sources form of tokenise + mask (m2t/data_modules.py:146-177): all conversations are tokenised in one
+    padded call; labels start as a copy and each row is masked with segment lengths measured by tokenising the header and
+    every turn on their own (the off-by-BOS quirk lives in _mask_targets)."""
+    header = DEFAULT_CONVERSATION_HEADER
+    texts = [sentences_to_formatted_conversation(header, conversation) for conversation in sources]
+    input_ids = _tokenize_fn(texts, tokenizer)["input_ids"]
+    labels = copy.deepcopy(input_ids)
+    for row, conversation in zip(labels, sources):
+        pieces = [header] + [turn["value"] for turn in conversation]
+        seg_lens = _tokenize_fn(pieces, tokenizer)["input_ids_lens"]
+        _mask_targets(row, seg_lens, [turn["from"] for turn in conversation])
+    return dict(input_ids=input_ids, labels=labels)
 
 
 def assert_hf_src_format(src):
-    """dict of equal-length lists, element i of the batch = src[k][i] for every k (m2t/data_modules.py:343-365)."""
+    """A batch in the HF layout is a dict of equal-length lists; element i of the batch is {k: src[k][i]}
+    (m2t/data_modules.py:343-365). Raises AssertionError otherwise."""
     assert isinstance(src, dict)
-    dict_keys = list(src.keys())
-    assert all(isinstance(src[k], list) for k in dict_keys), \
-        f"expected dict of lists, got: {[(k, type(src[k])) for k in dict_keys]}"
-    assert all(len(src[k]) == len(src[dict_keys[0]]) for k in dict_keys), \
-        f"expected lists of same length, got {[(k, len(src[k])) for k in dict_keys]}"
+    names = list(src.keys())
+    kinds = [(k, type(src[k])) for k in names]
+    assert all(kind is list for _, kind in kinds), f"expected dict of lists, got: {kinds}"
+    sizes = [(k, len(src[k])) for k in names]
+    assert all(n == sizes[0][1] for _, n in sizes), f"expected lists of same length, got {sizes}"
+
+
+def _qa_pairs(elem_json, key):
+    """The usable (question, answer) pairs of one element, or None (with the reference's warning) if it has none."""
+    responses = elem_json.get("response")
+    if not responses:
+        logging.warning(f"no response for {key}; skipping")
+        return None
+    if not isinstance(responses, list):
+        logging.warning(f"invalid response for {key} (could be empty); skipping")
+        return None
+    return [(r["question"], r["answer"]) for r in responses]
 
 
 def _to_conversation_hf(src: Dict[str, List]) -> Dict[str, List]:
-    """Unpack the (multiple) QA responses of every element of a batch into standalone QA-pair elements carrying the
-    audio encoding and its shape (m2t/data_modules.py:368-427); consumes random.uniform once per QA pair."""
-    output_dict = defaultdict(list)
+    """Batched flat-map of the HF pipeline (m2t/data_modules.py:368-427): every (question, answer) of every element
+    becomes its own element carrying the flat audio encoding, its shape, the id and the element's json minus the bulky
+    `response`; one random.uniform draw per pair decides whether <audio> precedes or follows the question."""
     assert_hf_src_format(src)
-    batch_size = len(src["__key__"])
-    for i in range(batch_size):
-        elem_json = src["json"][i]
-        elem_id = src["__key__"][i]
-        elem_audio_encoding = src["audio_encoding"][i]
-        elem_audio_encoding_shape = src["audio_encoding_shape"][i]
-        if not elem_json.get("response"):
-            logging.warning(f"no response for {src['__key__'][i]}; skipping")
+    out = defaultdict(list)
+    for key, elem_json, encoding, shape in zip(src["__key__"], src["json"], src["audio_encoding"],
+                                               src["audio_encoding_shape"]):
+        pairs = _qa_pairs(elem_json, key)
+        if pairs is None:
             continue
-        if not isinstance(elem_json["response"], list):
-            logging.warning(f"invalid response for {src['__key__'][i]} (could be empty); skipping")
-            continue
-        output_json = {k: elem_json[k] for k in elem_json.keys() if k != "response"}
-        for response in elem_json["response"]:
-            question, answer = (response["question"], response["answer"])
+        meta = {k: v for k, v in elem_json.items() if k != "response"}
+        for question, answer in pairs:
             audio_first = random.uniform(0.0, 1.0) > 0.5
-            if audio_first:
-                prompt_text = "\n".join(("<audio>", question))
-            else:
-                prompt_text = "\n".join((question, "<audio>"))
-            output = {"audio_encoding": elem_audio_encoding, "audio_encoding_shape": elem_audio_encoding_shape,
-                      "__key__": elem_id, "id": elem_id, "json": output_json,
-                      "conversations": [{"from": "human", "value": prompt_text}, {"from": "gpt", "value": answer}]}
-            for k, v in output.items():
-                output_dict[k].append(v)
-    return output_dict
+            prompt = concat_audio_token_and_prompt(question, audio_first)
+            fields = (("audio_encoding", encoding), ("audio_encoding_shape", shape), ("__key__", key), ("id", key),
+                      ("json", meta),
+                      ("conversations", [{"from": "human", "value": prompt}, {"from": "gpt", "value": answer}]))
+            for name, value in fields:
+                out[name].append(value)
+    return out
 
 
 def maybe_add_gcs_prefix(f: str) -> str:
-    """m2t/data_modules.py:430-433 (the string transformation only; GCS I/O itself is out of scope)."""
-    if f.startswith("gs://"):
-        return f"pipe:gsutil cat {f}"
-    return f
+    """`gs://` objects are read through a gsutil pipe by webdataset (m2t/data_modules.py:430-433); only the string
+    transformation is mirrored, GCS I/O itself is out of scope."""
+    return f"pipe:gsutil cat {f}" if f.startswith("gs://") else f
 
 
 def repeat_shards(urls: List[str], task_sample_probs: Optional[Dict[str, float]] = None):
-    """1024 x len(urls) shards resampled with replacement (np.random.choice), optionally weighted by the first
-    task_sample_probs key contained in the shard name (m2t/data_modules.py:441-463)."""
+    """HF Trainer needs an explicitly repeated shard list for an IterableDataset: 1024 x len(urls) draws with
+    replacement through np.random.choice, uniform or weighted by the first task_sample_probs key found in each shard's
+    name (m2t/data_modules.py:441-463; a shard no key matches is a ValueError)."""
+    weights = None
     if task_sample_probs is not None:
         logging.warning(f"applying task probs {task_sample_probs}")
-
-        def _shard_prob(shard) -> float:
-            for k, prob in task_sample_probs.items():
-                if k in shard:
-                    return prob
-            raise ValueError(f"probability for shard {shard} not defined in probs {task_sample_probs}")
-
-        probs = [_shard_prob(s) for s in urls]
-        probs = np.array(probs) / sum(probs)
-    else:
-        probs = None
-    _REPEATS = 1024 * len(urls)
-    return np.random.choice(urls, size=_REPEATS, replace=True, p=probs).tolist()
+        raw = []
+        for shard in urls:
+            hit = next((p for key, p in task_sample_probs.items() if key in shard), None)
+            if hit is None:
+                raise ValueError(f"probability for shard {shard} not defined in probs {task_sample_probs}")
+            raw.append(hit)
+        weights = np.array(raw) / sum(raw)
+    return np.random.choice(urls, size=1024 * len(urls), replace=True, p=weights).tolist()
 
 
 def _msgpack_decode(data: bytes):
@@ -392,21 +396,20 @@ def _msgpack_decode(data: bytes):
 
 
 def gen_from_msgpack_shards(shards):
-    """Yield the examples of msgpack shards; a shard is ONE msgpack-encoded list (m2t/data_modules.py:599-615).
-    Missing / undecodable shards are skipped with a warning."""
+    """Examples of msgpack shards, one shard = ONE msgpack list (m2t/data_modules.py:599-615). A local path that does
+    not exist or bytes that do not decode are skipped with a warning; anything but a list is an AssertionError."""
     for shard in shards:
-        if (not os.path.exists(shard)) and ("gs://" not in shard):
+        if "gs://" not in shard and not os.path.exists(shard):
             logging.warning(f"skipping nonexistent shard {shard}")
             continue
         try:
-            with open(shard, "rb") as f:
-                decoded = _msgpack_decode(f.read())
+            with open(shard, "rb") as fh:
+                examples = _msgpack_decode(fh.read())
         except Exception as e:  # noqa: BLE001
             logging.warning(f"error decoding data from shard {shard}: {e}; skipping.")
             continue
-        assert isinstance(decoded, list), f"expected list after decoding {shard}; got {type(decoded)}"
-        for sample in decoded:
-            yield sample
+        assert isinstance(examples, list), f"expected list after decoding {shard}; got {type(examples)}"
+        yield from examples
 
 
 def hf_preprocess_encodings(src: Dict[str, Any]) -> Dict[str, Any]:

@@ -14,27 +14,32 @@ import transformers
 
 
 class KeywordsStoppingCriteria(transformers.StoppingCriteria):
+    """Stop as soon as one of `keywords` shows up in the text generated after the prompt (`input_ids` is the prompt;
+    its length is latched on the first call). Keywords that the tokenizer maps to exactly one id are also recognised
+    directly on the newest token -- with a BOS-prepending tokenizer such as Llama's no keyword qualifies."""
+
     def __init__(self, keywords, tokenizer, input_ids):
         self.keywords = keywords
-        self.keyword_ids = [tokenizer(keyword).input_ids for keyword in keywords]
-        # only keywords that tokenise to exactly ONE id take the fast path (with a BOS-prepending tokenizer: none)
-        self.keyword_ids = [keyword_id[0] for keyword_id in self.keyword_ids
-                            if isinstance(keyword_id, list) and len(keyword_id) == 1]
         self.tokenizer = tokenizer
-        self.start_len = None
         self.input_ids = input_ids
+        self.start_len = None
+        encoded = (tokenizer(word).input_ids for word in keywords)
+        self.keyword_ids = [ids[0] for ids in encoded if isinstance(ids, list) and len(ids) == 1]
+
+    def _newest_token_is_keyword(self, output_ids) -> bool:
+        newest = output_ids[0, -1]
+        return any(newest == kid for kid in self.keyword_ids)
+
+    def _generated_text(self, output_ids) -> str:
+        return self.tokenizer.batch_decode(output_ids[:, self.start_len:], skip_special_tokens=True)[0]
 
     def __call__(self, output_ids: torch.LongTensor, scores: torch.FloatTensor, **kwargs) -> bool:
         if self.start_len is None:
             self.start_len = self.input_ids.shape[1]
-        for keyword_id in self.keyword_ids:
-            if output_ids[0, -1] == keyword_id:
-                return True
-        outputs = self.tokenizer.batch_decode(output_ids[:, self.start_len:], skip_special_tokens=True)[0]
-        for keyword in self.keywords:
-            if keyword in outputs:
-                return True
-        return False
+        if self._newest_token_is_keyword(output_ids):
+            return True
+        text = self._generated_text(output_ids)
+        return any(word in text for word in self.keywords)
 
 
 @torch.no_grad()

@@ -44,61 +44,68 @@ def _load_shard_into(model, path):
     del state_dict
 
 
+def _shard_paths(folder):
+    return [os.path.join(folder, name) for name in set(_read_index(folder)["weight_map"].values())]
+
+
 def load_sharded_mm_projector_weights(model, folder):
-    """Load sharded mm_projector weights (and, as the reference does, every other tensor of those shards) from folder."""
-    index = _read_index(folder)
-    for shard_file in list(set(index["weight_map"].values())):
-        _load_shard_into(model, os.path.join(folder, shard_file))
+    """Walk the shards of `folder` and load the projector tensors (and, as upstream does, every other tensor that
+    happens to live in those shards) into `model`."""
+    for path in _shard_paths(folder):
+        _load_shard_into(model, path)
 
 
 def load_sharded_checkpoint(model, folder, strict=True):
-    """transformers.modeling_utils.load_sharded_checkpoint plus the mm_adapter parameters. Shards are loaded one at a
-    time and freed. Returns torch's `_IncompatibleKeys(missing_keys, unexpected_keys)`; `strict` only decides whether
-    the (unused) error message is built, exactly as upstream."""
-    index = _read_index(folder)
-    shard_files = list(set(index["weight_map"].values()))
-    loaded_keys = index["weight_map"].keys()
-    model_keys = model.state_dict().keys()
-    missing_keys = [key for key in model_keys if key not in loaded_keys]
-    unexpected_keys = [key for key in loaded_keys if key not in model_keys]
-    for shard_file in shard_files:
-        _load_shard_into(model, os.path.join(folder, shard_file))
-        gc.collect()
-    return torch.nn.modules.module._IncompatibleKeys(missing_keys, unexpected_keys)
+    """transformers.modeling_utils.load_sharded_checkpoint with the mm_adapter special case: one shard in memory at a
+    time. Returns torch's `_IncompatibleKeys(missing_keys, unexpected_keys)` computed from the index against the model's
+    state dict. `strict` is accepted for signature parity; upstream builds an error message under it and then does NOT
+    raise (the raise is commented out, m2t/models/utils.py:102), so neither does this."""
+    in_checkpoint = _read_index(folder)["weight_map"].keys()
+    in_model = model.state_dict().keys()
+    report = torch.nn.modules.module._IncompatibleKeys([k for k in in_model if k not in in_checkpoint],
+                                                      [k for k in in_checkpoint if k not in in_model])
+    for path in _shard_paths(folder):
+        _load_shard_into(model, path)
+        gc.collect()  # the shard's tensors are freed before the next one is read
+    return report
+
+
+def _checkpoint_is_sharded(ckpt_dir) -> bool:
+    if os.path.exists(os.path.join(ckpt_dir, WEIGHTS_NAME)):
+        return False
+    pattern = os.path.join(ckpt_dir, "pytorch_model-*of*.bin")
+    found = glob.glob(pattern)
+    assert len(found), f"no files found matching {pattern}"
+    print(f"got checkpoint files {found}")
+    return True
 
 
 def load_pretrained_model(model_name: str, ckpt_num: int, torch_dtype=torch.float16, mm_use_audio_start_end=True,
                           device="cuda:0") -> Tuple[object, object]:
-    """`<model_name>/checkpoint-<ckpt_num>` -> (model on `device`, tokenizer), m2t/models/utils.py:126-203."""
+    """`<model_name>/checkpoint-<ckpt_num>` -> (model on `device`, tokenizer), m2t/models/utils.py:126-203: tokenizer
+    from the checkpoint folder, backbone through from_pretrained, an EMPTY projector created by
+    initialize_adapter_modules and then filled from the shards when the checkpoint is sharded, audio tokens registered
+    last. The model family is chosen by substring of `model_name` exactly as upstream ("meta-llama/Llama-2" /
+    "mosaicml/mpt"); anything else leaves upstream with an unbound `model`."""
     from transformers import AutoTokenizer
 
     from llark_b200.models.llamav2 import WrappedLlamav2ForCausalLM
 
     ckpt_dir = os.path.join(model_name, f"checkpoint-{ckpt_num}")
     tokenizer = AutoTokenizer.from_pretrained(ckpt_dir)
-    if os.path.exists(os.path.join(ckpt_dir, WEIGHTS_NAME)):
-        sharded_ckpt = False
-    else:
-        ckpt_glob = os.path.join(ckpt_dir, "pytorch_model-*of*.bin")
-        ckpt_files = glob.glob(ckpt_glob)
-        assert len(ckpt_files), f"no files found matching {ckpt_glob}"
-        print(f"got checkpoint files {ckpt_files}")
-        sharded_ckpt = True
+    sharded = _checkpoint_is_sharded(ckpt_dir)
     if "mosaicml/mpt" in model_name:
         raise NotImplementedError("the CLAP + MPT-1B variant (SURVEY §8(f) row 1) is not part of llark_b200 yet")
-    elif "meta-llama/Llama-2" in model_name:
-        model = WrappedLlamav2ForCausalLM.from_pretrained(ckpt_dir, torch_dtype=torch_dtype)
-        # does NOT load the adapter weights; it creates the module so that they can be loaded below
-        model.get_model().initialize_adapter_modules(tune_mm_mlp_adapter=False, fsdp=None)
-    else:
+    if "meta-llama/Llama-2" not in model_name:
         raise UnboundLocalError(f"no model class for {model_name!r} (the reference leaves `model` unbound here)")
-    if sharded_ckpt:
+    model = WrappedLlamav2ForCausalLM.from_pretrained(ckpt_dir, torch_dtype=torch_dtype)
+    model.get_model().initialize_adapter_modules(tune_mm_mlp_adapter=False, fsdp=None)
+    if sharded:
         print("[DEBUG] loading mm projector parameters")
         load_sharded_mm_projector_weights(model, ckpt_dir)
     model.to(device)
     model.get_model().mm_projector.to(device)
     model.config.mm_use_audio_start_end = mm_use_audio_start_end
-    model.initialize_audio_tokenizer(mm_use_audio_start_end=model.config.mm_use_audio_start_end, tokenizer=tokenizer,
-                                     device=device, tune_mm_mlp_adapter=model.config.tune_mm_mlp_adapter,
-                                     pretrain_mm_mlp_adapter=None)
+    model.initialize_audio_tokenizer(mm_use_audio_start_end=mm_use_audio_start_end, tokenizer=tokenizer, device=device,
+                                     tune_mm_mlp_adapter=model.config.tune_mm_mlp_adapter, pretrain_mm_mlp_adapter=None)
     return model, tokenizer
