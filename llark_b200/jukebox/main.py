@@ -179,3 +179,48 @@ def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0):
     vqvae = JukeboxVQVAE(cfg, vq_state)
     top_prior = JukeboxTopPrior(cfg, prior_state, precision=precision)
     return hps, vqvae, top_prior
+
+
+def _select_batch(paths, batch_size, batch_idx):
+    """The `--batch_size / --batch_idx` slice of the sorted input list (both must be given to take effect)."""
+    if batch_size is None or batch_idx is None:
+        return paths
+    starts = range(0, len(paths), batch_size)
+    if batch_idx >= len(starts):
+        raise ValueError("Invalid batch index")
+    return paths[starts[batch_idx]: starts[batch_idx] + batch_size]
+
+
+def main(argv=None):
+    """Command line of jukebox/main.py:203-256: embed every file of --input_dir (optionally one batch of it) and save
+    `<name>.npy` ([frames, 4800] float32, `.wav` in the name replaced) under --output_dir. The model is loaded lazily,
+    only once a first input exists."""
+    import os
+    import pathlib
+    from argparse import ArgumentParser
+
+    ap = ArgumentParser()
+    ap.add_argument("--batch_size", type=int, default=None)
+    ap.add_argument("--batch_idx", type=int, default=None)
+    ap.add_argument("--input_dir", default="/input", help="path to inputs")
+    ap.add_argument("--output_dir", default="/output", help="path to outputs")
+    ap.add_argument("--pool-frames-per-second", default=10, type=int,
+                    help="Frames per second for pooling. Set to zero to pool over all timesteps.")
+    args = ap.parse_args(argv)
+
+    out_dir = pathlib.Path(args.output_dir)
+    out_dir.mkdir(exist_ok=True)
+    inputs = _select_batch(sorted(pathlib.Path(args.input_dir).iterdir()), args.batch_size, args.batch_idx)
+    model = None
+    for path in inputs:
+        if model is None:
+            model = load_model()
+        hps, vqvae, top_prior = model
+        with torch.no_grad():
+            acts = get_acts_from_file(path, hps, vqvae, top_prior, meanpool=True,
+                                      pool_frames_per_second=args.pool_frames_per_second)
+        np.save(os.path.join(out_dir, os.path.basename(path).replace(".wav", ".npy")), acts)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,3 +106,36 @@ def test_hf_style_shard_dataset_pipeline(tmp_path):
     batch = coll([{"input_ids": o["input_ids"], "labels": o["labels"], "audio_encoding": o["audio_encoding"]}
                   for o in list(ds)[:3]])
     assert batch["input_ids"].shape[0] == 3 and batch["attention_mask"].dtype == torch.bool
+
+
+def test_jukebox_cli_batching_and_output_names(tmp_path, monkeypatch):
+    """jukebox/main.py:203-256: sorted inputs, --batch_size / --batch_idx slicing, `.wav` -> `.npy`, lazy model load,
+    "Invalid batch index". The embedding itself is stubbed (it needs the GPU; tests/test_jukebox_gpu.py covers it)."""
+    import llark_b200.jukebox.main as jm
+
+    inp, out = tmp_path / "in", tmp_path / "out"
+    inp.mkdir()
+    for name in ("c.wav", "a.wav", "b.wav", "d.wav", "e.wav"):
+        (inp / name).write_bytes(b"")
+    loads, seen = [], []
+    monkeypatch.setattr(jm, "load_model", lambda *a, **k: loads.append(1) or ("hps", "vq", "prior"))
+
+    def fake_acts(path, hps, vqvae, top_prior, meanpool=True, pool_frames_per_second=None):
+        seen.append((os.path.basename(str(path)), pool_frames_per_second, meanpool))
+        return np.full((2, 3), len(seen), dtype=np.float32)
+
+    monkeypatch.setattr(jm, "get_acts_from_file", fake_acts)
+    jm.main(["--input_dir", str(inp), "--output_dir", str(out), "--batch_size", "2", "--batch_idx", "1",
+             "--pool-frames-per-second", "5"])
+    assert seen == [("c.wav", 5, True), ("d.wav", 5, True)] and len(loads) == 1
+    assert sorted(os.listdir(out)) == ["c.npy", "d.npy"] and np.load(out / "d.npy")[0, 0] == 2
+    with pytest.raises(ValueError, match="Invalid batch index"):
+        jm.main(["--input_dir", str(inp), "--output_dir", str(out), "--batch_size", "2", "--batch_idx", "3"])
+    seen.clear()
+    jm.main(["--input_dir", str(inp), "--output_dir", str(out)])
+    assert [s[0] for s in seen] == ["a.wav", "b.wav", "c.wav", "d.wav", "e.wav"] and seen[0][1] == 10
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    n_loads = len(loads)
+    jm.main(["--input_dir", str(empty), "--output_dir", str(out)])
+    assert len(loads) == n_loads  # nothing to do -> the model is never built
