@@ -27,7 +27,7 @@ _ALIGN = 128  # elements (256 B): keeps every view 16-byte aligned for TMA and f
 class FlatBuckets:
     """Packs a list of (name, nn.Parameter) into one flat bf16 buffer, trainable parameters first."""
 
-    def __init__(self, named_params, device):
+    def __init__(self, named_params, device, cast_to_bf16=False):
         self.device = device
         self.entries = []  # (name, param, offset, numel)
         train = [(n, p) for n, p in named_params if p.requires_grad]
@@ -35,7 +35,7 @@ class FlatBuckets:
         off = 0
         for group in (train, frozen):
             for n, p in group:
-                if p.dtype != BF16:
+                if p.dtype != BF16 and not cast_to_bf16:
                     raise TypeError(
                         f"{n} is {p.dtype}: llark_b200 runs the reference's pure-bf16 regime (m2t/train.py:101-103); "
                         "cast the model with .to(torch.bfloat16) first")
@@ -51,7 +51,7 @@ class FlatBuckets:
         self.offsets = {n: (o, k) for n, _, o, k in self.entries}
         for n, p, o, k in self.entries:
             view = self.params[o:o + k].view(p.shape)
-            view.copy_(p.data)
+            view.copy_(p.data)  # converts when cast_to_bf16 admitted another storage dtype
             p.data = view
         self.grads_attached = False
         # set by the fused optimizer step: the bucket's contents have been consumed, so the next backward
@@ -180,7 +180,18 @@ class LlamaEngine:
         if dev.type != "cuda":
             raise RuntimeError("llark_b200 has no CPU path: move the model to a CUDA device (B200) first")
         if self.flat is None or not self.flat.is_current(named):
-            self.flat = FlatBuckets(named, dev)
+            # Inference scripts load the checkpoint in fp16 and run under torch.autocast(bfloat16)
+            # (m2t/models/utils.py:129, scripts/inference/infer_from_webdataset.py:82): every matmul then sees the
+            # weights rounded to bf16. With gradients disabled the bucket is built by that same rounding; training keeps
+            # the strict check (a silent down-cast of fp32 master weights would change the optimizer's regime).
+            cast = not torch.is_grad_enabled()
+            if cast and any(p.dtype != BF16 for _, p in named):
+                import logging
+
+                logging.warning("llark_b200: parameters held in %s are computed (and now stored) in bfloat16, as "
+                                "torch.autocast(bfloat16) computes them in the reference's inference scripts",
+                                sorted({str(p.dtype) for _, p in named if p.dtype != BF16}))
+            self.flat = FlatBuckets(named, dev, cast_to_bf16=cast)
         return self.flat
 
     def _tables(self, S, device):
