@@ -26,9 +26,8 @@ from oracle import ref_shims  # noqa: E402
 pytestmark = pytest.mark.skipif(not ref_shims.reference_available(), reason="the reference checkout is not present")
 
 
-@pytest.mark.parametrize("fixed_prompt", [None, "Describe the audio."])
-def test_reference_inference_script_runs_unchanged_over_llark_b200(tmp_path, monkeypatch, fixed_prompt):
-    import pandas as pd
+def _setup(tmp_path, monkeypatch):
+    """Aliases + CPU harness + a trained-looking sharded checkpoint and an eval shard; returns (name, shard)."""
     from transformers import AutoTokenizer
 
     import cpu_ops
@@ -92,11 +91,23 @@ def test_reference_inference_script_runs_unchanged_over_llark_b200(tmp_path, mon
     tok.save_pretrained(ck)
     shard = str(tmp_path / "eval-000000.tar")
     _shard(shard, rng, n=3)
+    return name, shard
 
+
+def _load_script(filename):
     spec = importlib.util.spec_from_file_location(
-        "ref_infer_script", os.path.join(ref_shims.REFERENCE_ROOT, "scripts", "inference", "infer_from_webdataset.py"))
+        "ref_" + filename[:-3], os.path.join(ref_shims.REFERENCE_ROOT, "scripts", "inference", filename))
     script = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(script)
+    return script
+
+
+@pytest.mark.parametrize("fixed_prompt", [None, "Describe the audio."])
+def test_reference_inference_script_runs_unchanged_over_llark_b200(tmp_path, monkeypatch, fixed_prompt):
+    import pandas as pd
+
+    name, shard = _setup(tmp_path, monkeypatch)
+    script = _load_script("infer_from_webdataset.py")
     from m2t.arguments import DataArguments, ModelArguments
 
     margs = ModelArguments(model_name_or_path=name, version="v0", mm_use_audio_start_end=True, mm_hidden_size=12)
@@ -114,3 +125,29 @@ def test_reference_inference_script_runs_unchanged_over_llark_b200(tmp_path, mon
         assert df["prompt_text"].str.contains("<audio_start>").all()     # the decoded prompt of each element
     else:
         assert (df["prompt_text"] == fixed_prompt).all()
+
+
+def test_reference_infer_from_encodings_script(tmp_path, monkeypatch):
+    """scripts/inference/infer_from_encodings.py::main(): a folder of `.npy` embeddings as the Jukebox CLI writes them
+    ([frames, width] float32 numpy arrays go straight into infer_with_prompt) + one fixed prompt."""
+    import numpy as np
+    import pandas as pd
+
+    name, _ = _setup(tmp_path, monkeypatch)
+    script = _load_script("infer_from_encodings.py")
+    from m2t.arguments import DataArguments, ModelArguments
+
+    enc_dir = tmp_path / "encodings"
+    enc_dir.mkdir()
+    g = np.random.default_rng(0)
+    for i in range(2):
+        np.save(enc_dir / f"clip{i}.npy", g.standard_normal((4, 12)).astype(np.float32))
+    margs = ModelArguments(model_name_or_path=name, version="v0", mm_use_audio_start_end=True, mm_hidden_size=12)
+    dargs = DataArguments(is_multimodal=True)
+    targs = types.SimpleNamespace(bits=16, bf16=True, fp16=False)
+    out = str(tmp_path / "res2" / "out.csv")
+    script.main(data_args=dargs, model_args=margs, training_args=targs, audio_encodings_dir=str(enc_dir), outfile=out,
+                ckpt_num=5, prompt="What instruments do you hear?", max_new_tokens=4)
+    df = pd.read_csv(out)
+    assert list(df.columns) == ["example_id", "prompt_text", "model_completion_text"] and len(df) == 2
+    assert (df["prompt_text"] == "What instruments do you hear?").all() and df["model_completion_text"].notna().all()
