@@ -304,3 +304,80 @@ def adamw_step(p, g, m, v, sumsq, lr, beta1, beta2, eps, weight_decay, step, gra
     v.copy_(vf.to(BF16))
     if zero_grad:
         g.zero_()
+
+
+# ------------------------------------------------------------------------------------------------ Jukebox front end
+import torch.nn.functional as _F  # noqa: E402
+
+
+def jb_conv_down(x, w, b):
+    return _F.conv1d(x, w, b, stride=2, padding=1)
+
+
+def jb_resblock(x, w1, b1, w2, b2, dilation):
+    h = _F.conv1d(torch.relu(x), w1, b1, padding=dilation, dilation=dilation)
+    return x + _F.conv1d(torch.relu(h), w2, b2)
+
+
+def jb_conv_k3(x, w, b):
+    return _F.conv1d(x, w, b, padding=1)
+
+
+def jb_vq_encode(x, codebook):
+    N, E, T = x.shape
+    flat = x.permute(0, 2, 1).reshape(N * T, E)
+    d = (flat * flat).sum(1, keepdim=True) - 2 * flat @ codebook.t() + (codebook * codebook).sum(1)[None]
+    return d.argmin(dim=1).view(N, T)
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, out_dtype=torch.float32, out=None):
+    return _F.layer_norm(x.float(), x.shape[-1:], gamma, beta, eps).to(out_dtype)
+
+
+def jb_embed_tokens(codes, emb, y_cond, pos_emb, x_cond, out=None):
+    N, T = codes.shape
+    x = emb[codes]
+    x = torch.roll(x, 1, dims=1)
+    x[:, 0] = y_cond
+    return ((x + pos_emb[None, :T]) + x_cond[None, :T]).reshape(N * T, -1)
+
+
+def jb_sparse_attn(qkv, N, T, heads, dh, block, pattern, out=None, out_dtype=torch.float32, exact=False):
+    A = heads * dh
+    q, k, v = qkv.float().view(N, T, 3, heads, dh).permute(2, 0, 3, 1, 4)  # [N, heads, T, dh]
+    nb = T // block
+
+    def dense(q_, k_, v_, causal):
+        s = (q_ @ k_.transpose(-1, -2)) / math.sqrt(dh)
+        if causal:
+            n = s.shape[-1]
+            s = s.masked_fill(~torch.ones(n, n, dtype=torch.bool).tril(), float("-inf"))
+        return torch.softmax(s, dim=-1) @ v_
+
+    if pattern == 0:
+        f = lambda t: t.reshape(N, heads, nb, block, dh)  # noqa: E731
+        a = dense(f(q), f(k), f(v), True).reshape(N, heads, T, dh)
+    elif pattern == 1:
+        f = lambda t: t.reshape(N, heads, nb, block, dh).transpose(2, 3)  # noqa: E731
+        a = dense(f(q), f(k), f(v), True).transpose(2, 3).reshape(N, heads, T, dh)
+    else:
+        qb = q.reshape(N, heads, nb, block, dh)
+        kb = k.reshape(N, heads, nb, block, dh)
+        vb = v.reshape(N, heads, nb, block, dh)
+        a = torch.zeros_like(qb)
+        a[:, :, 1:] = dense(qb[:, :, 1:], kb[:, :, :-1], vb[:, :, :-1], False)
+        a = a.reshape(N, heads, T, dh)
+    return a.permute(0, 2, 1, 3).reshape(N * T, A).to(out_dtype)
+
+
+def quick_gelu(x, out=None):
+    return x / (1 + torch.exp(-1.702 * x))
+
+
+def add3(a, b, c=None, out=None):
+    return (a + b) + c if c is not None else a + b
+
+
+def jb_pool(acts, T_valid, frame):
+    n = T_valid // frame
+    return acts[: n * frame].view(n, frame, -1).mean(1)
