@@ -115,8 +115,36 @@ class WrappedTrainer:
                 logging.warning(json.dumps(entry))
             save_steps = self._arg("save_steps", 0)
             if save_steps and self.state["global_step"] % save_steps == 0 and self._is_main():
-                self._save(os.path.join(self._arg("output_dir", "."), f"checkpoint-{self.state['global_step']}"))
+                ckpt = os.path.join(self._arg("output_dir", "."), f"checkpoint-{self.state['global_step']}")
+                self._save(ckpt)
+                self._save_optimizer(ckpt)
         return self.state
+
+    # ------------------------------------------------------------------------------------------ optimizer state
+    # transformers.Trainer writes optimizer.pt / scheduler.pt next to the weights of every checkpoint-N and restores
+    # them under resume_from_checkpoint (which m2t/train.py:257-258 requests whenever a checkpoint-* folder exists).
+    # Here the whole optimizer state is the two flat bf16 moment buffers and the step count; the cosine schedule is a
+    # pure function of global_step, so no scheduler file is needed.
+    def _save_optimizer(self, ckpt_dir):
+        opt = self.optimizer
+        torch.save({"exp_avg": opt.exp_avg.detach().cpu(), "exp_avg_sq": opt.exp_avg_sq.detach().cpu(),
+                    "step_count": opt.step_count, "global_step": self.state["global_step"],
+                    "n_train": int(opt.exp_avg.numel())}, os.path.join(ckpt_dir, "optimizer.pt"))
+        with open(os.path.join(ckpt_dir, "trainer_state.json"), "w") as f:
+            json.dump(self.state, f)
+
+    def _load_optimizer(self, ckpt_dir):
+        path = os.path.join(ckpt_dir, "optimizer.pt")
+        if not os.path.exists(path):
+            logging.warning(f"{path} not found: resuming with fresh AdamW moments")
+            return
+        st = torch.load(path, map_location="cpu")
+        opt = self.optimizer
+        if st["n_train"] != opt.exp_avg.numel():
+            raise ValueError("optimizer.pt does not match the model's trainable parameter bucket")
+        opt.exp_avg.copy_(st["exp_avg"])
+        opt.exp_avg_sq.copy_(st["exp_avg_sq"])
+        opt.step_count = int(st["step_count"])
 
     def _is_main(self):
         return int(os.environ.get("RANK", "0")) == 0
@@ -171,3 +199,9 @@ class WrappedTrainer:
         step = os.path.basename(os.path.normpath(path)).split("-")[-1]
         if step.isdigit():
             self.state["global_step"] = int(step)
+        state_file = os.path.join(path, "trainer_state.json")
+        if os.path.exists(state_file):
+            with open(state_file) as f:
+                self.state["log_history"] = json.load(f).get("log_history", [])
+        if self.optimizer is not None:
+            self._load_optimizer(path)

@@ -146,3 +146,76 @@ def test_engine_backward_and_optimizer_host_logic(cpu_engine, monkeypatch):
     with torch.no_grad():
         l1 = model(**batch).loss.item()
     assert l1 < l0
+
+
+def test_trainer_checkpoint_resume_is_exact(cpu_engine, monkeypatch, tmp_path):
+    """checkpoint-N (weights + optimizer.pt + trainer_state.json) -> a NEW trainer with resume_from_checkpoint=True must
+    land on exactly the parameters of an uninterrupted run (same data order, cosine schedule by global_step, AdamW
+    moments and step count restored)."""
+    from types import SimpleNamespace
+
+    import cpu_ops
+    import llark_b200.optim as optim
+    from llark_b200.trainer import WrappedTrainer
+    from oracle import llama_oracle as lo
+
+    monkeypatch.setattr(optim, "ops", cpu_ops)
+    cfg = lo.LlamaCfg()
+    params = lo.init_params(cfg, seed=0)
+    data = [lo.make_batch(cfg, B=1, S=32, F_frames=3, seed=s, pad_last=0) for s in range(4)]
+    samples = [{"input_ids": b["input_ids"][0], "labels": b["labels"][0], "audio_encoding": b["audio_encodings"][0]}
+               for b in data]
+
+    class Stream(torch.utils.data.IterableDataset):
+        def __init__(self, skip=0):
+            self.skip = skip
+
+        def __iter__(self):
+            i = self.skip
+            while True:
+                yield samples[i % len(samples)]
+                i += 1
+
+    def collate(items):
+        return {"input_ids": torch.stack([i["input_ids"] for i in items]),
+                "labels": torch.stack([i["labels"] for i in items]),
+                "attention_mask": torch.ones(len(items), 32, dtype=torch.bool),
+                "audio_encodings": torch.stack([i["audio_encoding"] for i in items])}
+
+    def make(out, max_steps, skip=0, save_steps=0):
+        model = _build(cfg, params)
+        for p in model.get_output_embeddings().parameters():
+            p.requires_grad = False
+        args = SimpleNamespace(max_steps=max_steps, per_device_train_batch_size=1, gradient_accumulation_steps=1,
+                               learning_rate=2e-3, warmup_ratio=0.25, max_grad_norm=1.0, weight_decay=0.0,
+                               logging_steps=1, save_steps=save_steps, output_dir=str(out), dataloader_num_workers=0,
+                               tune_mm_mlp_adapter=True)
+        return WrappedTrainer(model=model, tokenizer=None, args=args, train_dataset=Stream(skip), data_collator=collate)
+
+    straight = make(tmp_path / "a", 4)
+    straight.train()
+    ref = straight.model.engine.flat.params.clone()
+
+    # the interrupted run: same 4-step schedule, killed right after checkpoint-2 has been written
+    first = make(tmp_path / "b", 4, save_steps=2)
+
+    class Stop(Exception):
+        pass
+
+    real_save = first._save_optimizer
+
+    def save_then_stop(ckpt):
+        real_save(ckpt)
+        raise Stop()
+
+    first._save_optimizer = save_then_stop
+    with pytest.raises(Stop):
+        first.train()
+    assert {"optimizer.pt", "pytorch_model.bin", "trainer_state.json"} <= set(os.listdir(tmp_path / "b" / "checkpoint-2"))
+    assert os.path.exists(tmp_path / "b" / "mm_projector" / "checkpoint-2.bin")
+
+    resumed = make(tmp_path / "b", 4, skip=2)
+    resumed.train(resume_from_checkpoint=True)
+    assert resumed.state["global_step"] == 4 and len(resumed.state["log_history"]) == 4
+    assert resumed.optimizer.step_count == 4
+    assert torch.equal(resumed.model.engine.flat.params, ref)
