@@ -4,9 +4,10 @@
 //
 // Layout: packed projections qkv [B*S, 3*NH*128] bf16 (q heads | k heads | v heads per token row, RoPE already
 // applied in place), output O [B*S, NH*128] bf16, LSE [B, NH, S] fp32 (natural log; +inf marks a fully masked row).
-// Round-1 implementation: FA2-style tiling on mma.sync m16n8k16 bf16 (fp32 accumulate, online softmax in fp32,
-// exp2 with pre-scaled log2e). Attention is 1 % of step FLOPs at S = 512; the tcgen05/TMEM
-// version is a later-round upgrade and DESIGN.md says so.
+// This file: the C-ABI entry points and their dispatch, the FA2-style kernels on mma.sync m16n8k16 bf16 (fp32 accumulate,
+// online softmax in fp32, exp2 with pre-scaled log2e) that serve S > 4096 and `LLARK_ATTN_TC=0`, the dO.O row-sum
+// prep kernel of the backward pass, and the single-token decode kernel of the KV-cache path. The default path for
+// S <= 4096 is the tcgen05 / TMEM / TMA implementation in attention_tc.cu (same contract, same tests).
 #include "common.cuh"
 #include <stdlib.h>
 #include "../../include/llark_b200.h"
