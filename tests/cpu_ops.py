@@ -381,3 +381,70 @@ def add3(a, b, c=None, out=None):
 def jb_pool(acts, T_valid, frame):
     n = T_valid // frame
     return acts[: n * frame].view(n, frame, -1).mean(1)
+
+
+# ------------------------------------------------------------------------------------------------ MPT variant (staged ops)
+def ln_fwd(x, w, eps, mean=None, rstd=None, out=None, out_dtype=BF16):
+    """Bias-free LayerNorm over the last dim of a (possibly strided) [rows, W] view; fp32 statistics."""
+    xf = x.float()
+    mu = xf.mean(-1, keepdim=True)
+    r = torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+    if mean is not None:
+        mean.copy_(mu.flatten())
+    if rstd is not None:
+        rstd.copy_(r.flatten())
+    y = (((xf - mu) * r) * w.float()).to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def ln_bwd(x, w, dy, mean, rstd, dres, dx, dw, accumulate_dw):
+    xf, dyf, wf = x.float(), dy.float(), w.float()
+    xhat = (xf - mean.float()[:, None]) * rstd.float()[:, None]
+    g = dyf * wf
+    gx = rstd.float()[:, None] * (g - g.mean(-1, keepdim=True) - xhat * (g * xhat).mean(-1, keepdim=True))
+    if dres is not None:
+        gx = gx + dres.float()
+    dx.copy_(gx.to(dx.dtype))
+    if dw is not None:
+        d = (dyf * xhat).sum(0)
+        dw.copy_(((dw.float() if accumulate_dw else 0) + d).to(dw.dtype))
+    return dx
+
+
+def gelu_fwd(u):
+    return _F.gelu(u.float()).to(BF16)
+
+
+def gelu_bwd(u, dh):
+    uf = u.float()
+    cdf = 0.5 * (1 + torch.erf(uf / math.sqrt(2)))
+    pdf = torch.exp(-0.5 * uf * uf) / math.sqrt(2 * math.pi)
+    return (dh.float() * (cdf + uf * pdf)).to(BF16)
+
+
+def _alibi_attention(x, key_mask, B, S, n_heads, head_dim, slopes):
+    q, k, v = x.view(B, S, 3, n_heads, head_dim).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(head_dim)
+    sc = sc + (torch.arange(1 - S, 1, dtype=torch.float32).view(1, 1, 1, S) * slopes.float().view(1, n_heads, 1, 1))
+    allow = torch.ones(S, S, dtype=torch.bool).tril()[None, None]
+    if key_mask is not None:
+        allow = allow & key_mask.view(B, 1, 1, S).bool()
+    sc = sc.masked_fill(~allow, float("-inf"))
+    o = (torch.softmax(sc, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, n_heads * head_dim)
+    return o, sc
+
+
+def attn_alibi_fwd(qkv, key_mask, B, S, n_heads, head_dim, slopes):
+    o, sc = _alibi_attention(qkv.float(), key_mask, B, S, n_heads, head_dim, slopes)
+    return o.to(BF16), torch.logsumexp(sc, dim=-1)
+
+
+def attn_alibi_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, slopes):
+    x = qkv.float().clone().requires_grad_(True)
+    with torch.enable_grad():
+        o, _ = _alibi_attention(x, key_mask, B, S, n_heads, head_dim, slopes)
+        o.backward(dout.float())
+    return x.grad.to(BF16)

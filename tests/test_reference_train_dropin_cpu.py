@@ -134,3 +134,75 @@ def test_reference_train_py_runs_unchanged_over_llark_b200(tmp_path, monkeypatch
     # the side file keeps the projector and the embedding table (keys_to_match of m2t/models/trainer.py:112-120)
     assert {"model.mm_projector.bias", "model.mm_projector.weight"} <= set(sd)
     assert all(("mm_projector" in k) or ("embed_tokens" in k) for k in sd)
+
+
+def test_reference_train_py_takes_its_mpt_branch_over_llark_b200(tmp_path, monkeypatch):
+    """The `"mpt" in model_name_or_path` branch of m2t/train.py (WrappedMPTForCausalLM, fast tokenizer, tied embeddings):
+    same unchanged `train()`, with m2t.models.mpt aliased as well. HOST LOGIC ONLY -- five of the MPT ops have no CUDA
+    kernel yet (llark_b200/engine_mpt.py); the stand-in implements them in PyTorch for this run."""
+    import cpu_ops
+    import llark_b200.data_modules
+    import llark_b200.engine as eng
+    import llark_b200.engine_mpt as engm
+    import llark_b200.models.llamav2
+    import llark_b200.models.mpt
+    import llark_b200.optim as optim
+    import llark_b200.trainer
+    from llark_b200.models.mpt import WrappedMPTConfig, WrappedMPTForCausalLM
+    from tokenizers import Tokenizer, models, pre_tokenizers, trainers
+    from transformers import PreTrainedTokenizerFast
+
+    ref_shims.install()
+    for name, mod in (("m2t.models.llamav2", llark_b200.models.llamav2), ("m2t.models.mpt", llark_b200.models.mpt),
+                      ("m2t.data_modules", llark_b200.data_modules), ("m2t.models.trainer", llark_b200.trainer)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.delitem(sys.modules, "m2t.train", raising=False)
+    import m2t.train as ref_train
+    from m2t.arguments import DataArguments, ModelArguments
+
+    for mod in (eng, engm, optim):
+        monkeypatch.setattr(mod, "ops", cpu_ops)
+
+    def ensure_packed(self):
+        named = self._named()
+        if self.flat is None or not self.flat.is_current(named):
+            self.flat = eng.FlatBuckets(named, named[0][1].device)
+        return self.flat
+
+    monkeypatch.setattr(eng.LlamaEngine, "ensure_packed", ensure_packed)
+
+    rng = random.Random(1)
+    ck = str(tmp_path / "tiny-mpt-ckpt")
+    assert "llama" not in ck
+    corpus = [" ".join(rng.choices(WORDS, k=12)) + "." for _ in range(500)]
+    tk = Tokenizer(models.BPE(unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.train_from_iterator(corpus, trainers.BpeTrainer(vocab_size=300, special_tokens=["<unk>", "<|endoftext|>"],
+                                                       initial_alphabet=pre_tokenizers.ByteLevel.alphabet()))
+    fast = PreTrainedTokenizerFast(tokenizer_object=tk, eos_token="<|endoftext|>", unk_token="<unk>")  # no BOS, as GPT-NeoX
+    fast.save_pretrained(ck)
+    cfg = WrappedMPTConfig(d_model=256, n_heads=2, n_layers=2, vocab_size=len(fast), max_seq_len=1024, no_bias=True,
+                           attn_config={"alibi": True, "qk_ln": True, "attn_impl": "torch"})
+    torch.manual_seed(0)
+    WrappedMPTForCausalLM(cfg).save_pretrained(ck)
+    shard = str(tmp_path / "train-000000.tar")
+    _shard(shard, rng)
+    margs = ModelArguments(model_name_or_path=ck, version="v0", tune_mm_mlp_adapter=True, mm_use_audio_start_end=True,
+                           mm_hidden_size=12)
+    dargs = DataArguments(train_data_path=shard, is_multimodal=True)
+    targs = types.SimpleNamespace(
+        bits=16, bf16=True, fp16=False, lora_enable=False, cache_dir=None, model_max_length=512, fsdp=None,
+        freeze_mm_mlp_adapter=False, device=torch.device("cpu"), output_dir=str(tmp_path / "out"), local_rank=-1,
+        max_steps=3, per_device_train_batch_size=2, gradient_accumulation_steps=1, learning_rate=1e-3, weight_decay=0.0,
+        warmup_ratio=0.0, max_grad_norm=1.0, should_save=True, save_steps=0, logging_steps=1, dataloader_num_workers=0,
+        seed=0)
+    out = ref_train.train(model_args=margs, data_args=dargs, training_args=targs)
+    model = out["trainer"].model
+    assert type(model).__name__ == "WrappedMPTForCausalLM" and type(model).__module__ == "llark_b200.models.mpt"
+    assert model.get_input_embeddings() is model.get_output_embeddings()                     # tied
+    assert model.get_input_embeddings().weight.shape[0] == len(out["tokenizer"])
+    state = json.load(open(os.path.join(targs.output_dir, "trainer_state.json")))
+    hist = [h["loss"] for h in state["log_history"]]
+    assert len(hist) == 3 and hist[-1] < hist[0]
+    sd = torch.load(os.path.join(targs.output_dir, "pytorch_model.bin"))
+    assert "transformer.blocks.1.attn.q_ln.weight" in sd and "transformer.mm_projector.weight" in sd
