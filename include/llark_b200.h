@@ -118,6 +118,28 @@ int llark_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows
  * Backward writes dq|dk|dv into dqkv (same packing). workspace: llark_attn_bwd_workspace bytes. */
 int llark_attn_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
                    int head_dim, float scale, cudaStream_t stream);
+/* ALiBi variant of the causal attention for the CLAP + MPT-1B path (m2t/llava/model/mpt/attention.py:31-83,458-484):
+ * scores = q.k * scale + slopes[h] * (key - (S - 1)); packed qkv WITHOUT RoPE; slopes fp32 [n_heads]; otherwise the contract of
+ * llark_attn_fwd / llark_attn_bwd (workspace: llark_attn_bwd_workspace bytes). S <= 4096. */
+int llark_attn_alibi_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse, const float* slopes,
+                         int B, int S, int n_heads, int head_dim, float scale, cudaStream_t stream);
+int llark_attn_alibi_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                         const float* lse, void* dqkv, const float* slopes, int B, int S, int n_heads, int head_dim,
+                         float scale, void* workspace, cudaStream_t stream);
+/* Bias-free LayerNorm over bf16 rows with row strides (elements) ldx / ldy: y = bf16(((x - mean) * rstd) * w), fp32
+ * statistics written to mean / rstd (may be NULL). LPLayerNorm (m2t/llava/model/mpt/norm.py:26-52) and the q_ln / k_ln
+ * of attention.py:289-292. Backward: dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w; dw (bf16
+ * [W], may be NULL) receives (or accumulates) sum_rows dy * xhat; dres is a dense [rows, W] tensor or NULL. */
+int llark_ln_fwd(const void* x, long long ldx, const void* w, void* y, long long ldy, float* mean, float* rstd,
+                 long long rows, int W, float eps, cudaStream_t stream);
+long long llark_ln_bwd_workspace(long long rows, int W);
+int llark_ln_bwd(const void* x, long long ldx, const void* w, const void* dy, long long lddy, const float* mean,
+                 const float* rstd, const void* dres, void* dx, long long lddx, void* dw, int accumulate_dw, long long rows,
+                 int W, void* workspace, cudaStream_t stream);
+/* Exact GELU (nn.GELU(approximate="none"), m2t/llava/model/mpt/blocks.py:14) and its backward du = dh * (Phi(u) +
+ * u * phi(u)); bf16, n a multiple of 8. */
+int llark_gelu_fwd(const void* u, void* h, long long n, cudaStream_t stream);
+int llark_gelu_bwd(const void* u, const void* dh, void* du, long long n, cudaStream_t stream);
 /* Single-token decode step against a KV cache (transformers' cached LlamaAttention behind m2t/infer.py's
  * model.generate): q [B, n_heads*128] (RoPE applied), k_cache / v_cache [B, s_max, n_heads*128] bf16, lens int32 [B] =
  * valid cached positions per row including the new token (<= s_max <= 4096), out [B, n_heads*128]. */

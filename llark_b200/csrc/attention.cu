@@ -19,6 +19,12 @@ int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out
                        float scale, cudaStream_t st);  // attention_tc.cu
 int attn_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
                        const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, cudaStream_t st);
+// ALiBi instantiation (attention_tc_alibi.cu) for the MPT variant: same kernels + slope_h * key on the scores
+int attn_alibi_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S,
+                             int n_heads, float scale, const float* slopes, cudaStream_t st);
+int attn_alibi_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
+                             const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, const float* slopes,
+                             cudaStream_t st);
 // LLARK_ATTN_TC bit 0: tcgen05 forward, bit 1: tcgen05 backward. Default 3 (both, validated on B200: same test
 // tolerances as the mma.sync kernels, forward 202 -> 89 us and backward 717 -> 481 us at B 16, S 512, 32 heads);
 // 0 selects the mma.sync kernels of this file (also used for S > 4096).
@@ -687,4 +693,28 @@ extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, co
     attn_bwd_dq_kernel<<<grid, 128, DQ_SMEM, st>>>((const __nv_bfloat16*)qkv, key_mask, (const __nv_bfloat16*)dout, lse,
                                                    Dsum, (__nv_bfloat16*)dqkv, S, n_heads, scale, scale * LOG2E);
     return check_launch2();
+}
+
+// ---------------------------------------------------------------------------------------------- ALiBi (MPT variant)
+// STAGED (not yet run on a B200). Causal attention with key-padding mask and the ALiBi bias of MPT
+// (m2t/llava/model/mpt/attention.py:31-83, 458-484): scores = q.k / sqrt(128) + slopes[h] * (key - (S - 1)). Same layouts as
+// llark_attn_fwd / llark_attn_bwd (packed qkv without RoPE, LSE, Dsum workspace); tcgen05 kernels only (S <= 4096).
+extern "C" int llark_attn_alibi_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse,
+                                    const float* slopes, int B, int S, int n_heads, int head_dim, float scale,
+                                    cudaStream_t st) {
+    if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0 || !slopes) return LLARK_EINVAL;
+    return attn_alibi_fwd_tc_launch(qkv, key_mask, out, lse, B, S, n_heads, scale, slopes, st);
+}
+extern "C" int llark_attn_alibi_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                                    const float* lse, void* dqkv, const float* slopes, int B, int S, int n_heads,
+                                    int head_dim, float scale, void* workspace, cudaStream_t st) {
+    if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0 || !workspace || !slopes) return LLARK_EINVAL;
+    float* Dsum = (float*)workspace;
+    const long long warps = (long long)B * S * n_heads;
+    attn_bwd_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out,
+                                                                                (const __nv_bfloat16*)dout, Dsum, B, S,
+                                                                                n_heads);
+    int rc = check_launch2();
+    if (rc) return rc;
+    return attn_alibi_bwd_tc_launch(qkv, key_mask, dout, lse, Dsum, dqkv, B, S, n_heads, scale, slopes, st);
 }

@@ -27,7 +27,23 @@ extern thread_local int g_last_cuda_error;
 int tensor_map_2d(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
                   int box_outer, int elem_bytes);  // gemm_tcgen05.cu (cached cuTensorMapEncodeTiled, 128 B swizzle)
 
-namespace atc {
+// This file is also compiled a second time by attention_tc_alibi.cu with LLARK_ATC_ALIBI defined: same kernels with an
+// ALiBi bias slope_h * key added to the scaled scores (MPT variant, no RoPE involved). Without the macro the
+// preprocessed text -- and therefore the generated code of the Llama path -- is exactly what it was before.
+#ifndef LLARK_ATC_NS
+#define LLARK_ATC_NS atc
+#define LLARK_ATC_FWD_LAUNCH attn_fwd_tc_launch
+#define LLARK_ATC_BWD_LAUNCH attn_bwd_tc_launch
+#endif
+#ifdef LLARK_ATC_ALIBI
+#define LLARK_ATC_SLOPES_PARAM , const float* __restrict__ alibi_slopes
+#define LLARK_ATC_SLOPES_ARG , alibi_slopes
+#else
+#define LLARK_ATC_SLOPES_PARAM
+#define LLARK_ATC_SLOPES_ARG
+#endif
+
+namespace LLARK_ATC_NS {
 
 constexpr int HD = 128;
 constexpr int BQ = 128;         // query rows per CTA
@@ -87,7 +103,8 @@ struct Ring {
 
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned char* __restrict__ mask,
-                   __nv_bfloat16* __restrict__ O, float* __restrict__ lse_out, int S, int NH, float scale_log2) {
+                   __nv_bfloat16* __restrict__ O, float* __restrict__ lse_out, int S, int NH, float scale_log2
+                   LLARK_ATC_SLOPES_PARAM) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -243,6 +260,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
             const int k0 = j * BK;
             const uint32_t mw0 = maskw[2 * j], mw1 = maskw[2 * j + 1];
             const bool plain = (k0 + BK - 1 <= q0 + quad * 32) && mw0 == 0xffffffffu && mw1 == 0xffffffffu;  // warp-uniform
+#ifdef LLARK_ATC_ALIBI
+            // ALiBi variant: v = s * scale * log2e + slope_h * log2e * (key - (S - 1)) (the reference's bias, <= 0) is formed first (the bias differs per key, so
+            // the row max has to be taken over v, not over the raw scores); masked entries -> -inf
+            const float slope2 = alibi_slopes[h] * LOG2E;
+            float rmax = -INFINITY;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t mw = hh ? mw1 : mw0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int key = k0 + hh * 32 + c;
+                    const bool ok = plain || (key <= qi && ((mw >> c) & 1u));
+                    const float v = ok ? fmaf(__uint_as_float(sv[hh][c]), scale_log2, slope2 * (float)(key - (S - 1))) : -INFINITY;
+                    sv[hh][c] = __float_as_uint(v);
+                    rmax = fmaxf(rmax, v);
+                }
+            }
+            const float m_cand = fmaxf(m_run, rmax);
+            const bool move = (m_cand > m_run + 8.f) || (m_run == -INFINITY);
+            const float m_new = move ? m_cand : m_run;
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = ex2(m_run - m_use);
+            m_run = m_new;
+            float psum = 0.f;
+            uint32_t pk[32];  // 64 bf16 probabilities
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = ex2(__uint_as_float(sv[hh][c]) - m_use);
+                    const float p1 = ex2(__uint_as_float(sv[hh][c + 1]) - m_use);
+                    psum += p0 + p1;
+                    pk[hh * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
+                }
+#else
             // row max of the RAW scores (scale > 0, so the max commutes with the scaling); masked entries -> -inf
             float rmax = -INFINITY;
             if (plain) {
@@ -284,6 +336,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const unsigned ch
                     psum += p0 + p1;
                     pk[hh * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
                 }
+#endif
             l_run = l_run * alpha + psum;
 
             if (j > 0) {
@@ -438,7 +491,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                       const unsigned char* __restrict__ mask, const float* __restrict__ lse,
                       const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
-                      float scale_log2) {
+                      float scale_log2 LLARK_ATC_SLOPES_PARAM) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -587,7 +640,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 const bool ok = plain || (kbase + c <= qi && ((mw >> c) & 1u));
+#ifdef LLARK_ATC_ALIBI
+                const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2,
+                                             fmaf(alibi_slopes[h] * LOG2E, (float)(kbase + c - (S - 1)), -lse2))) : 0.f;
+#else
                 const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2, -lse2)) : 0.f;
+#endif
                 ds[c] = p * (__uint_as_float(dv[c]) - dsum);
             }
             if (j >= 2) {
@@ -629,7 +687,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const unsigned char* __restrict__ mask, const float* __restrict__ lse,
                         const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
-                        float scale_log2) {
+                        float scale_log2 LLARK_ATC_SLOPES_PARAM) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -787,7 +845,12 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 const bool ok = kvalid && (plain || qc0 + c >= key);
+#ifdef LLARK_ATC_ALIBI
+                const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2,
+                                             fmaf(alibi_slopes[h] * LOG2E, (float)(key - (S - 1)), -rv[g * 32 + c]))) : 0.f;
+#else
                 const float p = ok ? ex2(fmaf(__uint_as_float(sv[c]), scale_log2, -rv[g * 32 + c])) : 0.f;
+#endif
                 pt[c] = p;
                 ds[c] = p * (__uint_as_float(dv[c]) - rv[64 + g * 32 + c]);
             }
@@ -821,13 +884,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
 }
 
-}  // namespace atc
+}  // namespace LLARK_ATC_NS (atc)
 
 // Returns LLARK_OK when the tcgen05 kernel was launched, LLARK_EINVAL when the shape is outside its envelope
 // (the caller then uses the mma.sync kernel).
-int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
-                       float scale, cudaStream_t st) {
-    using namespace atc;
+int LLARK_ATC_FWD_LAUNCH(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
+                       float scale LLARK_ATC_SLOPES_PARAM, cudaStream_t st) {
+    using namespace LLARK_ATC_NS;
     if (S > MAX_S || (long long)B * S > 0x7fffffffLL) return LLARK_EINVAL;
     CUtensorMap tm;
     const long long ld = 3LL * n_heads * HD;
@@ -844,7 +907,7 @@ int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out
     }
     dim3 grid((S + BQ - 1) / BQ, n_heads, B);
     attn_fwd_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tm, key_mask, (__nv_bfloat16*)out, lse, S, n_heads,
-                                                           scale * LOG2E);
+                                                           scale * LOG2E LLARK_ATC_SLOPES_ARG);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         g_last_cuda_error = (int)e;
@@ -855,9 +918,10 @@ int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out
 
 // Backward (dq|dk|dv into dqkv) on tcgen05; Dsum must already hold rowsum(dO o O). LLARK_EINVAL = shape outside the
 // envelope (caller falls back to the mma.sync kernels).
-int attn_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
-                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, cudaStream_t st) {
-    using namespace atc;
+int LLARK_ATC_BWD_LAUNCH(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
+                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale LLARK_ATC_SLOPES_PARAM,
+                       cudaStream_t st) {
+    using namespace LLARK_ATC_NS;
     if ((long long)B * S > 0x7fffffffLL || S > MAX_S) return LLARK_EINVAL;
     CUtensorMap tq, td;
     const long long ld = 3LL * n_heads * HD, ldo = (long long)n_heads * HD;
@@ -879,9 +943,9 @@ int attn_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const voi
     }
     dim3 grid((S + BQ - 1) / BQ, n_heads, B);
     attn_bwd_dkdv_tc_kernel<<<grid, kBwdThreads, KV_SMEM_BYTES, st>>>(tq, td, key_mask, lse, Dsum, (__nv_bfloat16*)dqkv,
-                                                                      S, n_heads, scale, scale * LOG2E);
+                                                                      S, n_heads, scale, scale * LOG2E LLARK_ATC_SLOPES_ARG);
     attn_bwd_dq_tc_kernel<<<grid, kBwdThreads, DQ_SMEM_BYTES, st>>>(tq, td, key_mask, lse, Dsum, (__nv_bfloat16*)dqkv, S,
-                                                                    n_heads, scale, scale * LOG2E);
+                                                                    n_heads, scale, scale * LOG2E LLARK_ATC_SLOPES_ARG);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         g_last_cuda_error = (int)e;

@@ -198,6 +198,52 @@ def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, 
     return dqkv
 
 
+# ------------------------------------------------------------------------------------------------ MPT variant (staged)
+def attn_alibi_fwd(qkv, key_mask, B, S, n_heads, head_dim, slopes, out=None, lse=None):
+    out = out if out is not None else torch.empty((B * S, n_heads * head_dim), device=qkv.device, dtype=BF16)
+    lse = lse if lse is not None else torch.empty((B, n_heads, S), device=qkv.device, dtype=torch.float32)
+    check(lib().llark_attn_alibi_fwd(_p(qkv), _p(key_mask), _p(out), _p(lse), _p(slopes), B, S, n_heads, head_dim,
+                                     1.0 / math.sqrt(head_dim), _stream()), "attn_alibi_fwd")
+    return out, lse
+
+
+def attn_alibi_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, slopes, dqkv=None):
+    dqkv = dqkv if dqkv is not None else torch.empty_like(qkv)
+    ws = torch.empty(lib().llark_attn_bwd_workspace(B, S, n_heads), device=qkv.device, dtype=torch.uint8)
+    check(lib().llark_attn_alibi_bwd(_p(qkv), _p(key_mask), _p(out), _p(dout), _p(lse), _p(dqkv), _p(slopes), B, S,
+                                     n_heads, head_dim, 1.0 / math.sqrt(head_dim), _p(ws), _stream()), "attn_alibi_bwd")
+    return dqkv
+
+
+def ln_fwd(x, w, eps, mean=None, rstd=None, out=None, out_dtype=BF16):
+    """Bias-free LayerNorm of the rows of a [rows, W] bf16 view (row stride = x.stride(0)); out may be a strided view."""
+    rows, W = x.shape
+    out = out if out is not None else torch.empty((rows, W), device=x.device, dtype=BF16)
+    check(lib().llark_ln_fwd(_p(x), x.stride(0), _p(w), _p(out), out.stride(0), _p(mean), _p(rstd), rows, W, eps,
+                             _stream()), "ln_fwd")
+    return out
+
+
+def ln_bwd(x, w, dy, mean, rstd, dres, dx, dw, accumulate_dw):
+    rows, W = x.shape
+    ws = torch.empty(lib().llark_ln_bwd_workspace(rows, W), device=x.device, dtype=torch.uint8) if dw is not None else None
+    check(lib().llark_ln_bwd(_p(x), x.stride(0), _p(w), _p(dy), dy.stride(0), _p(mean), _p(rstd), _p(dres), _p(dx),
+                             dx.stride(0), _p(dw), int(accumulate_dw), rows, W, _p(ws), _stream()), "ln_bwd")
+    return dx
+
+
+def gelu_fwd(u, out=None):
+    out = out if out is not None else torch.empty_like(u)
+    check(lib().llark_gelu_fwd(_p(u), _p(out), u.numel(), _stream()), "gelu_fwd")
+    return out
+
+
+def gelu_bwd(u, dh, out=None):
+    out = out if out is not None else torch.empty_like(u)
+    check(lib().llark_gelu_bwd(_p(u), _p(dh), _p(out), u.numel(), _stream()), "gelu_bwd")
+    return out
+
+
 def colsum(x, out, accumulate=False):
     rows, H = x.shape
     check(lib().llark_colsum(_p(x), _p(out), rows, H, int(accumulate), _stream()), "colsum")
