@@ -169,6 +169,11 @@ class LlamaEngine:
         # RoPE and SwiGLU-backward fused into GEMM epilogues (llark_gemm_ex); LLARK_FUSE_EPILOGUES=0 keeps the
         # separate llark_rope / llark_swiglu_bwd kernels (same results bit for bit)
         self.fuse_epilogues = os.environ.get("LLARK_FUSE_EPILOGUES", "1") != "0"
+        # Activation recompute (the reference's --gradient_checkpointing True, m2t/models/llamav2.py:241,255-257):
+        # "auto" = only when the model's gradient_checkpointing flag is set AND the saved activations of the step would
+        # not fit comfortably in free HBM (a 7B step at S=512, B=16 keeps 35 GB and does not need it); "1" / "0" force it.
+        self.recompute = os.environ.get("LLARK_RECOMPUTE", "auto")
+        self.recomputed_last_step = False
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -225,6 +230,56 @@ class LlamaEngine:
             anchor = flat.entries[0][1]  # first trainable parameter
             return _StepFn.apply(anchor, self, batch)
         return self._forward(batch, need_grad=False)
+
+    # ------------------------------------------------------------------------------------------ one decoder layer
+    def _layer_forward(self, l, x, mask_u8, B, S, cos, sin, kv_sink=None):
+        """Forward of decoder layer l on x [B*S, H]; returns (x_out, tensors the backward needs, kernels launched)."""
+        cfg, flat = self.cfg, self.flat
+        H, I, NH = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+        D = H // NH
+        M, dev, eps = B * S, x.device, cfg.rms_norm_eps
+        n = 0
+        pfx = f"model.layers.{l}."
+        w_in = flat.pview(pfx + "input_layernorm.weight")
+        w_post = flat.pview(pfx + "post_attention_layernorm.weight")
+        Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
+        Wo = flat.pview(pfx + "self_attn.o_proj.weight", (H, H))
+        Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
+        Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
+        rstd1 = torch.empty(M, device=dev, dtype=torch.float32)
+        xn1 = ops.rmsnorm_fwd(x, w_in, eps, rstd=rstd1)
+        if self.fuse_epilogues and D == 128:
+            # RoPE of the q | k heads in the QKV projection's epilogue (bit-identical to gemm -> llark_rope)
+            qkv = ops.gemm(xn1, Wqkv, rope=(cos, sin, S, 2 * H))
+        else:
+            qkv = ops.gemm(xn1, Wqkv)
+            ops.rope_(qkv, cos, sin, S, NH, D)
+            n += 1
+        if kv_sink is not None:  # prefill of the generation path: keep the (post-RoPE) keys and the values
+            q3 = qkv.view(B, S, 3, H)
+            kv_sink.k[l][:, :S].copy_(q3[:, :, 1])
+            kv_sink.v[l][:, :S].copy_(q3[:, :, 2])
+        attn, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
+        x_mid = ops.gemm(attn, Wo, residual=x)
+        rstd2 = torch.empty(M, device=dev, dtype=torch.float32)
+        xn2 = ops.rmsnorm_fwd(x_mid, w_post, eps, rstd=rstd2)
+        gu = ops.gemm(xn2, Wgu)
+        act = ops.swiglu_fwd(gu)
+        x_out = ops.gemm(act, Wd, residual=x_mid)
+        n += 8
+        return x_out, (x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act), n
+
+    def _want_recompute(self, M, dev):
+        if self.recompute in ("0", "1"):
+            return self.recompute == "1"
+        if not getattr(self.lm.model, "gradient_checkpointing", False) or dev.type != "cuda":
+            return False
+        cfg = self.cfg
+        per_token = 2 * (8 * cfg.hidden_size + 3 * cfg.intermediate_size)  # bytes of bf16 activations kept per layer
+        need = M * cfg.num_hidden_layers * per_token
+        free, _ = torch.cuda.mem_get_info(dev)
+        free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)  # cached blocks are reusable
+        return need > 0.6 * free
 
     # ------------------------------------------------------------------------------------------ forward
     def _forward(self, batch, need_grad, kv_sink=None):
@@ -292,37 +347,15 @@ class LlamaEngine:
             saved.update(enc_bf=None, frames=None, audio_off=None, start_pos=None, n_feat=0)
 
         cos, sin = self._tables(S, dev)
+        recompute = need_grad and self._want_recompute(M, dev)
+        self.recomputed_last_step = recompute
         for l in range(L):
-            pfx = f"model.layers.{l}."
-            w_in = flat.pview(pfx + "input_layernorm.weight")
-            w_post = flat.pview(pfx + "post_attention_layernorm.weight")
-            Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
-            Wo = flat.pview(pfx + "self_attn.o_proj.weight", (H, H))
-            Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
-            Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
-            rstd1 = torch.empty(M, device=dev, dtype=torch.float32)
-            xn1 = ops.rmsnorm_fwd(x, w_in, eps, rstd=rstd1)
-            if self.fuse_epilogues and D == 128:
-                # RoPE of the q | k heads in the QKV projection's epilogue (bit-identical to gemm -> llark_rope)
-                qkv = ops.gemm(xn1, Wqkv, rope=(cos, sin, S, 2 * H))
-            else:
-                qkv = ops.gemm(xn1, Wqkv)
-                ops.rope_(qkv, cos, sin, S, NH, D)
-                n0 += 1
-            if kv_sink is not None:  # prefill of the generation path: keep the (post-RoPE) keys and the values
-                q3 = qkv.view(B, S, 3, H)
-                kv_sink.k[l][:, :S].copy_(q3[:, :, 1])
-                kv_sink.v[l][:, :S].copy_(q3[:, :, 2])
-            attn, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
-            x_mid = ops.gemm(attn, Wo, residual=x)
-            rstd2 = torch.empty(M, device=dev, dtype=torch.float32)
-            xn2 = ops.rmsnorm_fwd(x_mid, w_post, eps, rstd=rstd2)
-            gu = ops.gemm(xn2, Wgu)
-            act = ops.swiglu_fwd(gu)
-            x_out = ops.gemm(act, Wd, residual=x_mid)
-            n0 += 8
+            x_out, keep, n = self._layer_forward(l, x, mask_u8, B, S, cos, sin, kv_sink)
+            n0 += n
             if need_grad:
-                saved["layers"].append((x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act))
+                # with recompute only the layer's input survives the forward; _backward regenerates the rest
+                saved["layers"].append((x,) if recompute else keep)
+            del keep
             x = x_out
 
         w_norm = flat.pview("model.norm.weight")
@@ -469,8 +502,13 @@ class LlamaEngine:
 
         for l in reversed(range(L)):
             pfx = f"model.layers.{l}."
-            x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act = sv["layers"][l]
+            kept = sv["layers"][l]
             sv["layers"][l] = None
+            if len(kept) == 1:  # activation recompute: same kernels on the same input -> the same bits as the forward
+                _, kept, n = self._layer_forward(l, kept[0], sv["mask"], B, S, cos, sin)
+                n0 += n
+            x, rstd1, xn1, qkv, attn, lse, x_mid, rstd2, xn2, gu, act = kept
+            del kept
             Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
             Wo = flat.pview(pfx + "self_attn.o_proj.weight", (H, H))
             Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)

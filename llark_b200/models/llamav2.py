@@ -87,7 +87,8 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         return self.model
 
     def _set_gradient_checkpointing(self, module, value=False):
-        # Activations of a 7B step at S=512 fit in 180 GB without recompute; the flag is accepted and recorded.
+        # The engine recomputes a layer's activations in the backward only when this flag is set AND the step's saved
+        # activations would not fit in free HBM (LlamaEngine._want_recompute; a 7B step at S=512, B=16 keeps 35 GB).
         if isinstance(module, WrappedLlamav2Model):
             module.gradient_checkpointing = value
 

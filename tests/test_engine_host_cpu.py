@@ -148,6 +148,33 @@ def test_engine_backward_and_optimizer_host_logic(cpu_engine, monkeypatch):
     assert l1 < l0
 
 
+def test_activation_recompute_gives_the_same_gradients(cpu_engine):
+    """--gradient_checkpointing True (m2t/models/llamav2.py:241,255-257): with recompute the forward keeps one tensor per
+    layer and the backward regenerates the rest with the same kernels -- same loss, same gradient bits, more launches."""
+    from oracle import llama_oracle as lo
+
+    cfg = lo.LlamaCfg()
+    params = lo.init_params(cfg, seed=0)
+    batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=3)
+    results = []
+    for mode in ("0", "1", "auto"):
+        model = _build(cfg, params)
+        model.engine.recompute = mode
+        if mode == "auto":
+            model.gradient_checkpointing_enable()   # flag set, but nothing to save on this tiny CPU run -> no recompute
+        out = model(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+        kept = [len(t) for t in model.engine._saved["layers"]]
+        out.loss.backward()
+        results.append((out.loss.item(), model.engine.flat.grads.clone(), model.engine.launches, kept,
+                        model.engine.recomputed_last_step))
+    (l0, g0, n0, k0, r0), (l1, g1, n1, k1, r1), (l2, g2, n2, k2, r2) = results
+    assert (r0, r1, r2) == (False, True, False)
+    assert set(k0) == {11} and set(k1) == {1} and k2 == k0
+    assert l0 == l1 == l2
+    assert torch.equal(g0, g1) and torch.equal(g0, g2)
+    assert n1 == n0 + 8 * cfg.num_layers and n2 == n0
+
+
 def test_trainer_checkpoint_resume_is_exact(cpu_engine, monkeypatch, tmp_path):
     """checkpoint-N (weights + optimizer.pt + trainer_state.json) -> a NEW trainer with resume_from_checkpoint=True must
     land on exactly the parameters of an uninterrupted run (same data order, cosine schedule by global_step, AdamW

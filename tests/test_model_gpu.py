@@ -274,3 +274,23 @@ def test_generate_with_kv_cache_matches_cacheless():
     finally:
         os.environ.pop("LLARK_KV_CACHE", None)
     assert torch.equal(got, ref)
+
+
+@STAGED
+def test_activation_recompute_is_bit_identical_on_gpu(gold):
+    """LLARK_RECOMPUTE=1 (what --gradient_checkpointing True selects under memory pressure): the backward regenerates each
+    layer's activations from its input with the same kernels, so loss and every gradient match the plain step bit for
+    bit. Written after the round's GPU budget was spent (the CPU stand-in version of this test runs in the CPU suite)."""
+    from oracle import llama_oracle as lo
+
+    cfg = lo.LlamaCfg(**gold["cfg"])
+    batch = _to_cuda(lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=0))
+    res = []
+    for mode in ("0", "1"):
+        model = build_model(cfg, lo.init_params(cfg, seed=0))
+        model.engine.recompute = mode
+        out = model(**batch)
+        out.loss.backward()
+        res.append((out.loss.item(), model.engine.flat.grads.clone(), model.engine.recomputed_last_step))
+    assert [r[2] for r in res] == [False, True]
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
