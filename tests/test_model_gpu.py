@@ -294,3 +294,17 @@ def test_activation_recompute_is_bit_identical_on_gpu(gold):
         res.append((out.loss.item(), model.engine.flat.grads.clone(), model.engine.recomputed_last_step))
     assert [r[2] for r in res] == [False, True]
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+
+
+@STAGED
+def test_wrapped_trainer_follows_the_reference_trajectory_on_gpu(tmp_path):
+    """GPU twin of tests/test_trainstep_cpu.py: WrappedTrainer + the fused AdamW kernel on the CUDA engine against the
+    reference's 4-step trajectory (tests/golden/trainstep_ref.pt). Written after the round's GPU budget was spent."""
+    from oracle import llama_oracle as lo
+    from test_trainstep_cpu import GOLD as TRAJ, check_against_reference, run_trajectory
+
+    gold_t = torch.load(TRAJ, weights_only=False)
+    cfg = lo.LlamaCfg(**gold_t["cfg"])
+    model = build_model(cfg, lo.init_params(cfg, seed=gold_t["seed"]), detach_text=True)
+    trainer = run_trajectory(model, gold_t, tmp_path)
+    check_against_reference(trainer, model, gold_t, loss_tol=1e-2, delta_tol=0.05, cos_min=0.98)
