@@ -303,6 +303,17 @@ def test_attention_fwd_bwd(B, S, NH, pad):
         assert _rel(got[:, :, i], g[:, :, i]) < 1.5e-2, name
 
 
+@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
+                    reason="sizes not yet run on a B200 (set LLARK_STAGED=1)")
+@pytest.mark.parametrize("B,S,NH,pad", [(1, 2048, 2, True),     # the reference's --model_max_length (train_llark.sh)
+                                        (1, 4096, 1, False),    # upper edge of the tcgen05 kernels' envelope
+                                        (1, 4160, 1, True)])    # beyond it: llark_attn_* must fall back to mma.sync
+def test_attention_fwd_bwd_long_sequences(B, S, NH, pad):
+    """Maximum sizes: same check as test_attention_fwd_bwd at the reference's model_max_length, at the largest S the
+    tcgen05 kernels accept (MAX_S in attention_tc.cu) and one tile past it (the mma.sync kernels take over)."""
+    test_attention_fwd_bwd(B, S, NH, pad)
+
+
 def test_embed_splice_fwd_bwd_and_flags():
     ops = _ops()
     torch.manual_seed(7)
