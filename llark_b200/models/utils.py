@@ -5,8 +5,7 @@ function names, arguments and behaviour (pure host logic, tested on CPU against 
     load_sharded_checkpoint             :55-123  (transformers' loader + the mm_projector special case; like the reference
                                                   it computes missing / unexpected keys but never raises on them: the
                                                   `raise` is commented out upstream, :102)
-    load_pretrained_model               :126-203 (Llama-2 branch; the MPT branch belongs to the CLAP + MPT variant,
-                                                  §8(f) row 1, which is not built: NotImplementedError)
+    load_pretrained_model               :126-203 (both branches: "meta-llama/Llama-2" and "mosaicml/mpt" in the name)
 The on-disk layout is HF's: `pytorch_model.bin` or `pytorch_model-XXXXX-of-YYYYY.bin` shards listed in
 `pytorch_model.bin.index.json` (`weight_map`), projector tensors under `model.mm_projector.{weight,bias}`.
 """
@@ -94,18 +93,37 @@ def load_pretrained_model(model_name: str, ckpt_num: int, torch_dtype=torch.floa
     ckpt_dir = os.path.join(model_name, f"checkpoint-{ckpt_num}")
     tokenizer = AutoTokenizer.from_pretrained(ckpt_dir)
     sharded = _checkpoint_is_sharded(ckpt_dir)
-    if "mosaicml/mpt" in model_name:
-        raise NotImplementedError("the CLAP + MPT-1B variant (SURVEY §8(f) row 1) is not part of llark_b200 yet")
-    if "meta-llama/Llama-2" not in model_name:
+    is_mpt = "mosaicml/mpt" in model_name
+    if is_mpt:
+        # CLAP + MPT-1B variant (:149-169): single-file checkpoints only -- upstream reads `ckpt_file`, which it binds
+        # only when pytorch_model.bin exists, so a sharded MPT checkpoint dies there with a NameError too.
+        from llark_b200.models.mpt import WrappedMPTForCausalLM
+
+        if sharded:
+            raise NameError("name 'ckpt_file' is not defined (the reference's MPT branch needs an unsharded checkpoint)")
+        ckpt_file = os.path.join(ckpt_dir, WEIGHTS_NAME)
+        model = WrappedMPTForCausalLM.from_pretrained(ckpt_dir, torch_dtype=torch_dtype)
+        model.get_model().initialize_adapter_modules(tune_mm_mlp_adapter=False, pretrain_mm_mlp_adapter=ckpt_file,
+                                                     fsdp=None)
+        print(f"[DEBUG] loading {ckpt_file} weights manually")
+        model.load_state_dict(torch.load(ckpt_file, map_location="cpu"))
+        model.config.mm_use_audio_start_end = True
+        aec = model.transformer.audio_encoder_config
+        aec.audio_start_token, aec.audio_end_token = tokenizer.convert_tokens_to_ids(
+            [DEFAULT_AUDIO_START_TOKEN, DEFAULT_AUDIO_END_TOKEN])
+    elif "meta-llama/Llama-2" in model_name:
+        model = WrappedLlamav2ForCausalLM.from_pretrained(ckpt_dir, torch_dtype=torch_dtype)
+        model.get_model().initialize_adapter_modules(tune_mm_mlp_adapter=False, fsdp=None)
+    else:
         raise UnboundLocalError(f"no model class for {model_name!r} (the reference leaves `model` unbound here)")
-    model = WrappedLlamav2ForCausalLM.from_pretrained(ckpt_dir, torch_dtype=torch_dtype)
-    model.get_model().initialize_adapter_modules(tune_mm_mlp_adapter=False, fsdp=None)
     if sharded:
         print("[DEBUG] loading mm projector parameters")
         load_sharded_mm_projector_weights(model, ckpt_dir)
     model.to(device)
     model.get_model().mm_projector.to(device)
     model.config.mm_use_audio_start_end = mm_use_audio_start_end
-    model.initialize_audio_tokenizer(mm_use_audio_start_end=mm_use_audio_start_end, tokenizer=tokenizer, device=device,
-                                     tune_mm_mlp_adapter=model.config.tune_mm_mlp_adapter, pretrain_mm_mlp_adapter=None)
+    if not is_mpt:  # :190-197 -- the MPT checkpoint already carries its audio tokens and their ids
+        model.initialize_audio_tokenizer(mm_use_audio_start_end=mm_use_audio_start_end, tokenizer=tokenizer,
+                                         device=device, tune_mm_mlp_adapter=model.config.tune_mm_mlp_adapter,
+                                         pretrain_mm_mlp_adapter=None)
     return model, tokenizer

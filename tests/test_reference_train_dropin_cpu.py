@@ -206,3 +206,47 @@ def test_reference_train_py_takes_its_mpt_branch_over_llark_b200(tmp_path, monke
     assert len(hist) == 3 and hist[-1] < hist[0]
     sd = torch.load(os.path.join(targs.output_dir, "pytorch_model.bin"))
     assert "transformer.blocks.1.attn.q_ln.weight" in sd and "transformer.mm_projector.weight" in sd
+
+    # ... and what that run leaves behind loads through the MPT branch of load_pretrained_model
+    # (m2t/models/utils.py:149-169: from_pretrained -> projector from pytorch_model.bin -> whole state dict -> audio token
+    # ids from the tokenizer; no initialize_audio_tokenizer), as the inference scripts do with torch_dtype=float16
+    import llark_b200.models.utils as mutils
+
+    name = str(tmp_path / "mosaicml" / "mpt-tiny")
+    ck3 = os.path.join(name, "checkpoint-3")
+    os.makedirs(ck3)
+    out["tokenizer"].save_pretrained(ck3)
+    model.config.save_pretrained(ck3)
+    torch.save(sd, os.path.join(ck3, "pytorch_model.bin"))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+
+    def ensure_packed_any_dtype(self):
+        named = self._named()
+        if self.flat is None or not self.flat.is_current(named):
+            self.flat = eng.FlatBuckets(named, named[0][1].device, cast_to_bf16=not torch.is_grad_enabled())
+        return self.flat
+
+    monkeypatch.setattr(eng.LlamaEngine, "ensure_packed", ensure_packed_any_dtype)
+    loaded, tok = mutils.load_pretrained_model(name, 3, torch_dtype=torch.float16, device="cpu")
+    assert type(loaded).__module__ == "llark_b200.models.mpt" and len(tok) == len(out["tokenizer"])
+    lsd = loaded.state_dict()
+    assert set(lsd) == set(sd)
+    for k in ("transformer.mm_projector.weight", "transformer.mm_projector.bias", "transformer.wte.weight",
+              "transformer.blocks.0.attn.Wqkv.weight"):
+        assert torch.equal(lsd[k].float(), sd[k].to(torch.float16).float()), k
+    aec = loaded.transformer.audio_encoder_config
+    assert [aec.audio_start_token, aec.audio_end_token] == tok.convert_tokens_to_ids(["<audio_start>", "<audio_end>"])
+    assert loaded.config.mm_use_audio_start_end is True
+    ids = torch.tensor([[5, 6, aec.audio_start_token, tok.convert_tokens_to_ids("<audio_patch>"), aec.audio_end_token, 7, 8]])
+    enc = torch.randn(1, 1, 12, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        a = loaded(input_ids=ids, audio_encodings=enc).logits.float()
+        b = model(input_ids=ids, audio_encodings=enc).logits.float()
+    assert ((a - b).norm() / b.norm()).item() < 3e-2          # fp16-loaded weights rounded to bf16 vs the bf16 originals
+    other = tmp_path / "other" / "model" / "checkpoint-3"       # neither family in the name: `model` stays unbound upstream
+    os.makedirs(other)
+    out["tokenizer"].save_pretrained(str(other))
+    torch.save({}, other / "pytorch_model.bin")
+    with pytest.raises(UnboundLocalError):
+        mutils.load_pretrained_model(str(tmp_path / "other" / "model"), 3)
