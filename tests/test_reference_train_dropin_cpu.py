@@ -234,7 +234,9 @@ def test_reference_train_py_takes_its_mpt_branch_over_llark_b200(tmp_path, monke
     assert set(lsd) == set(sd)
     for k in ("transformer.mm_projector.weight", "transformer.mm_projector.bias", "transformer.wte.weight",
               "transformer.blocks.0.attn.Wqkv.weight"):
-        assert torch.equal(lsd[k].float(), sd[k].to(torch.float16).float()), k
+        # backbone tensors arrive through from_pretrained(torch_dtype=float16); the projector is created afterwards in
+        # the default dtype and filled from the bf16 file -- either way within one fp16 rounding of what was saved
+        assert torch.allclose(lsd[k].float(), sd[k].float(), rtol=1e-3, atol=1e-4), k
     aec = loaded.transformer.audio_encoder_config
     assert [aec.audio_start_token, aec.audio_end_token] == tok.convert_tokens_to_ids(["<audio_start>", "<audio_end>"])
     assert loaded.config.mm_use_audio_start_end is True
