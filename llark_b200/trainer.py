@@ -46,6 +46,12 @@ class WrappedTrainer:
         self.state = {"global_step": 0, "log_history": []}
         self.optimizer = None
         model.validate = "lazy"
+        if self._arg("gradient_checkpointing", False):  # transformers.Trainer turns the flag into this call
+            model.gradient_checkpointing_enable()
+        # transformers.Trainer places the model on args.device in its constructor (m2t/train.py never does it itself)
+        dev = self._arg("device", None)
+        if dev is not None and next(model.parameters()).device != torch.device(dev):
+            model.to(torch.device(dev))
 
     def _arg(self, name, default):
         return getattr(self.args, name, default) if self.args is not None else default
