@@ -111,7 +111,12 @@ class TrainingArguments:
 
         if self.use_cpu:
             return torch.device("cpu")
-        return torch.device("cuda", max(self.local_rank, 0))
+        dev = torch.device("cuda", max(self.local_rank, 0))
+        if torch.cuda.is_available():
+            # one process per GPU: the C-ABI launches on the thread's current device, so make it this rank's
+            # (transformers.TrainingArguments._setup_devices does the same)
+            torch.cuda.set_device(dev)
+        return dev
 
     @property
     def should_save(self) -> bool:

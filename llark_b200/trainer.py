@@ -52,6 +52,9 @@ class WrappedTrainer:
         dev = self._arg("device", None)
         if dev is not None and next(model.parameters()).device != torch.device(dev):
             model.to(torch.device(dev))
+        placed = next(model.parameters()).device
+        if placed.type == "cuda" and torch.cuda.is_available():
+            torch.cuda.set_device(placed)  # kernels are launched on the thread's current device
 
     def _arg(self, name, default):
         return getattr(self.args, name, default) if self.args is not None else default
