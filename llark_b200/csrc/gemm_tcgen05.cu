@@ -793,6 +793,7 @@ static int get_tensor_map_mn4(CUtensorMap* out, const void* ptr, long long mn, l
         return LLARK_EDRIVER;
     }
     std::lock_guard<std::mutex> lk(g_mu);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();  // bounded: variable sequence lengths create new keys
     g_map_cache[key] = *out;
     return LLARK_OK;
 }
@@ -827,6 +828,7 @@ static int get_tensor_map_mn3(CUtensorMap* out, const void* ptr, long long mn, l
         return LLARK_EDRIVER;
     }
     std::lock_guard<std::mutex> lk(g_mu);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();  // bounded: variable sequence lengths create new keys
     g_map_cache[key] = *out;
     return LLARK_OK;
 }
