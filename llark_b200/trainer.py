@@ -127,7 +127,27 @@ class WrappedTrainer:
                 ckpt = os.path.join(self._arg("output_dir", "."), f"checkpoint-{self.state['global_step']}")
                 self._save(ckpt)
                 self._save_optimizer(ckpt)
+                self._rotate_checkpoints()
         return self.state
+
+    def _rotate_checkpoints(self):
+        """--save_total_limit N (train_llark.sh passes 1): keep the N most recent checkpoint-* folders of output_dir, as
+        transformers.Trainer._rotate_checkpoints does; the mm_projector/checkpoint-N.bin side files are not rotated."""
+        import re
+        import shutil
+
+        limit = self._arg("save_total_limit", None)
+        if limit is None or limit <= 0:
+            return
+        out = self._arg("output_dir", ".")
+        found = []
+        for name in os.listdir(out):
+            m = re.fullmatch(r"checkpoint-(\d+)", name)
+            if m and os.path.isdir(os.path.join(out, name)):
+                found.append((int(m.group(1)), name))
+        for _, name in sorted(found)[:-limit]:
+            logging.warning(f"deleting older checkpoint {name} (save_total_limit={limit})")
+            shutil.rmtree(os.path.join(out, name), ignore_errors=True)
 
     # ------------------------------------------------------------------------------------------ optimizer state
     # transformers.Trainer writes optimizer.pt / scheduler.pt next to the weights of every checkpoint-N and restores

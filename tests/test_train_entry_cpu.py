@@ -82,8 +82,11 @@ def test_own_train_entry_point_runs_and_resumes(tmp_path, monkeypatch):
     hist = json.load(open(os.path.join(out_dir, "trainer_state.json")))["log_history"]
     assert [h["step"] for h in hist] == [1, 2, 3, 4] and hist[-1]["loss"] < hist[0]["loss"]
 
-    # second launch with a larger budget: output_dir holds checkpoints -> resume from the latest (step 4), 2 more steps
+    # second launch with a larger budget: output_dir holds checkpoints -> resume from the latest (step 4), 2 more steps;
+    # --save_total_limit 1 (as train_llark.sh) leaves only the newest checkpoint folder, the projector side files stay
     argv[argv.index("--max_steps") + 1] = "6"
-    again = entry.main(argv)["trainer"]
+    again = entry.main(argv + ["--save_total_limit", "1"])["trainer"]
+    assert sorted(n for n in os.listdir(out_dir) if n.startswith("checkpoint-")) == ["checkpoint-6"]
+    assert {"checkpoint-2.bin", "checkpoint-4.bin", "checkpoint-6.bin"} <= set(os.listdir(os.path.join(out_dir, "mm_projector")))
     steps = [h["step"] for h in again.state["log_history"]]
     assert again.state["global_step"] == 6 and steps[-2:] == [5, 6] and again.optimizer.step_count == 6
