@@ -46,6 +46,15 @@ class WrappedTrainer:
         self.state = {"global_step": 0, "log_history": []}
         self.optimizer = None
         model.validate = "lazy"
+        seed = self._arg("seed", None)
+        if seed is not None:  # transformers.Trainer.__init__ calls set_seed(args.seed): python, numpy and torch generators
+            import random
+
+            import numpy as np
+
+            random.seed(seed)
+            np.random.seed(seed)
+            torch.manual_seed(seed)
         if self._arg("gradient_checkpointing", False):  # transformers.Trainer turns the flag into this call
             model.gradient_checkpointing_enable()
         # transformers.Trainer places the model on args.device in its constructor (m2t/train.py never does it itself)
