@@ -13,7 +13,6 @@ Reference semantics reproduced: pure-bf16 weights/grads
 non-ignored shifted tokens computed on bf16 logits, lm_head frozen when requires_grad is False, text-token
 embedding rows detached when `orig_embeds_params` is set (m2t/models/llamav2.py:176-198).
 """
-import math
 import os
 
 import torch

@@ -7,7 +7,6 @@ STATUS: STAGED. The modules hold parameters; `forward` runs llark_b200.engine_mp
 on CPU against the pinned oracle; the kernels only this variant needs (mpt_ops.cu, attention_tc_alibi.cu) compile for
 sm_100a but have not run on a B200 yet (tests/test_mpt_gpu.py, LLARK_STAGED=1). Supported configuration = what MPT-1B uses: multi-head attention with
 ALiBi and q/k LayerNorm, low-precision LayerNorm, no biases, tied embeddings, no logit scale, attn_impl irrelevant."""
-import os
 from typing import List, Optional, Tuple
 
 import torch

@@ -10,7 +10,6 @@ the forward pass's argmax 31 on the fixture). use_cache=False is the faithful ru
 by construction) and is what the fixture records."""
 import os
 import sys
-import types
 
 import torch
 

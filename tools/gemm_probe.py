@@ -1,6 +1,7 @@
 """GEMM probe: prints a relative-error table for a ladder of shapes (one operand-major combination per process,
 so a trap in one combination cannot poison the others). Usage: python tools/gemm_probe.py <a_mn> <b_mn> <fp32>"""
-import sys, os, time
+import os
+import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from llark_b200 import ops
