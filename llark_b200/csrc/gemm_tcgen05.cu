@@ -991,9 +991,6 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
     if (rc != LLARK_OK) return rc;
 
     const int two_cta = llark_gemm_get_mode();
-    const int a_box_rows = BLOCK_M;                 // A rows per CTA (both modes)
-    const int b_box_rows = two_cta ? 128 : BLOCK_N; // B rows (N) per CTA
-    (void)a_box_rows;
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.C = C; p.ldc = ldc; p.c_fp32 = c_fp32;
