@@ -72,3 +72,41 @@ def greedy_generate(step_logits: Callable[[torch.Tensor], torch.Tensor], input_i
         if stop or not bool(unfinished.any()):
             break
     return input_ids
+
+
+@torch.no_grad()
+def generate_with_model(model, step_logits: Callable[[torch.Tensor], torch.Tensor], inputs=None, input_ids=None,
+                        stopping_criteria=None, max_new_tokens=None, max_length=None, do_sample=None, num_beams=None,
+                        eos_token_id=None, pad_token_id=None) -> torch.Tensor:
+    """The argument handling of `model.generate(...)` shared by the Llama and MPT wrappers: resolves the prompt, the
+    token budget (max_new_tokens, else max_length / generation_config.max_length / 20 as transformers) and the eos /
+    pad ids (argument, generation_config, config), switches the module to eval for the duration, and runs
+    greedy_generate with the caller's `step_logits`. Sampling and beam search are refused."""
+    if input_ids is None:
+        input_ids = inputs
+    if input_ids is None:
+        raise ValueError("generate needs input_ids")
+    if do_sample or (num_beams not in (None, 1)):
+        raise NotImplementedError("llark_b200 generates greedily (do_sample=False, num_beams=1)")
+    gc = getattr(model, "generation_config", None)
+    if max_new_tokens is None:
+        total = max_length if max_length is not None else (getattr(gc, "max_length", None) or 20)
+        max_new_tokens = max(int(total) - input_ids.shape[1], 0)
+    if eos_token_id is None:
+        eos_token_id = getattr(gc, "eos_token_id", None)
+        if eos_token_id is None:
+            eos_token_id = getattr(model.config, "eos_token_id", None)
+    if isinstance(eos_token_id, int):
+        eos_token_id = [eos_token_id]
+    if pad_token_id is None:
+        pad_token_id = getattr(gc, "pad_token_id", None)
+    if pad_token_id is None:
+        pad_token_id = getattr(model.config, "pad_token_id", None)
+    was_training = model.training
+    model.eval()
+    try:
+        return greedy_generate(step_logits, input_ids, max_new_tokens, eos_token_id=eos_token_id,
+                               stopping_criteria=list(stopping_criteria or []), pad_token_id=pad_token_id)
+    finally:
+        model.train(was_training)
+

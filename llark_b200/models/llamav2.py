@@ -192,30 +192,7 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         [B, prompt + new] like GenerationMixin. Sampling / beam search are not built. No KV cache yet: each step is a
         full forward over the sequence so far (llark_b200/generate.py); extra keyword arguments the reference passes
         along (`labels`, `example_id`, `id`) are ignored as transformers ignores / rejects them."""
-        from llark_b200.generate import greedy_generate
-
-        if input_ids is None:
-            input_ids = inputs
-        if input_ids is None:
-            raise ValueError("generate needs input_ids")
-        if do_sample or (num_beams not in (None, 1)):
-            raise NotImplementedError("llark_b200 generates greedily (do_sample=False, num_beams=1)")
-        gc = getattr(self, "generation_config", None)
-        if max_new_tokens is None:
-            total = max_length if max_length is not None else (getattr(gc, "max_length", None) or 20)
-            max_new_tokens = max(int(total) - input_ids.shape[1], 0)
-        if eos_token_id is None:
-            eos_token_id = getattr(gc, "eos_token_id", None)
-            if eos_token_id is None:
-                eos_token_id = getattr(self.config, "eos_token_id", None)
-        if isinstance(eos_token_id, int):
-            eos_token_id = [eos_token_id]
-        if pad_token_id is None:
-            pad_token_id = getattr(gc, "pad_token_id", None)
-        if pad_token_id is None:
-            pad_token_id = getattr(self.config, "pad_token_id", None)
-        was_training = self.training
-        self.eval()
+        from llark_b200.generate import generate_with_model
 
         state = {"cache": None}
 
@@ -228,11 +205,10 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
             out = self.forward(input_ids=ids, audio_encodings=audio_encodings, use_cache=False, return_dict=True)
             return out.logits[:, -1, :]
 
-        try:
-            return greedy_generate(step_logits, input_ids, max_new_tokens, eos_token_id=eos_token_id,
-                                   stopping_criteria=list(stopping_criteria or []), pad_token_id=pad_token_id)
-        finally:
-            self.train(was_training)
+        return generate_with_model(self, step_logits, inputs=inputs, input_ids=input_ids,
+                                   stopping_criteria=stopping_criteria, max_new_tokens=max_new_tokens,
+                                   max_length=max_length, do_sample=do_sample, num_beams=num_beams,
+                                   eos_token_id=eos_token_id, pad_token_id=pad_token_id)
 
     def initialize_audio_tokenizer(self, mm_use_audio_start_end, tokenizer, device, tune_mm_mlp_adapter=False,
                                    pretrain_mm_mlp_adapter=None):

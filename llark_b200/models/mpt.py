@@ -215,6 +215,24 @@ class WrappedMPTForCausalLM(WrappedMPTPreTrainedModel, GenerationMixin):
             self._engine.check_flags()
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=None)
 
+    @torch.no_grad()
+    def generate(self, inputs=None, input_ids=None, audio_encodings=None, stopping_criteria=None, max_new_tokens=None,
+                 max_length=None, do_sample=None, num_beams=None, eos_token_id=None, pad_token_id=None, **kwargs):
+        """`model.generate(input_ids=, audio_encodings=, stopping_criteria=[...], max_new_tokens=...)` as m2t/infer.py:146-152
+        calls it: greedy, one full forward per new token (no KV cache for this variant), full sequences returned."""
+        from llark_b200.generate import generate_with_model
+
+        del kwargs  # labels / example_id / id ride along from infer_with_prompt(**elem)
+
+        def step_logits(ids):
+            return self.forward(input_ids=ids, audio_encodings=audio_encodings, use_cache=False,
+                                return_dict=True).logits[:, -1, :]
+
+        return generate_with_model(self, step_logits, inputs=inputs, input_ids=input_ids,
+                                   stopping_criteria=stopping_criteria, max_new_tokens=max_new_tokens,
+                                   max_length=max_length, do_sample=do_sample, num_beams=num_beams,
+                                   eos_token_id=eos_token_id, pad_token_id=pad_token_id)
+
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
         """m2t/models/mpt.py:337-365."""
         if inputs_embeds is not None:

@@ -246,6 +246,18 @@ def test_reference_train_py_takes_its_mpt_branch_over_llark_b200(tmp_path, monke
         a = loaded(input_ids=ids, audio_encodings=enc).logits.float()
         b = model(input_ids=ids, audio_encodings=enc).logits.float()
     assert ((a - b).norm() / b.norm()).item() < 3e-2          # fp16-loaded weights rounded to bf16 vs the bf16 originals
+    # greedy, cache-less generate of the MPT wrapper == argmax of repeated full forwards (what m2t/infer.py:146-152 needs)
+    got = loaded.generate(input_ids=ids, audio_encodings=enc, max_new_tokens=3, labels=None, example_id="x")
+    want = ids.clone()
+    with torch.no_grad():
+        for _ in range(3):
+            nxt = loaded(input_ids=want, audio_encodings=enc).logits[:, -1].float().argmax(-1)
+            want = torch.cat([want, nxt[:, None]], dim=1)
+            if nxt.item() == tok.eos_token_id:
+                break
+    assert torch.equal(got[:, : want.shape[1]], want) and got.shape[1] <= ids.shape[1] + 3
+    with pytest.raises(NotImplementedError):
+        loaded.generate(input_ids=ids, audio_encodings=enc, do_sample=True)
     other = tmp_path / "other" / "model" / "checkpoint-3"       # neither family in the name: `model` stays unbound upstream
     os.makedirs(other)
     out["tokenizer"].save_pretrained(str(other))
