@@ -63,6 +63,23 @@ def test_gemm_bf16(M, N, K, a_mn, b_mn, gemm_mode):
     assert _rel(out, ref) < 5e-3, (err, scale)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
+                    reason="shapes not yet run on a B200 (set LLARK_STAGED=1)")
+@pytest.mark.parametrize("M,N,K", [(1, 12288, 4096), (2, 2048, 512), (17, 4096, 11008), (32, 50372, 2048)])
+def test_gemm_very_few_rows(M, N, K, gemm_mode):
+    """Fewer A rows than one TMA box (the box reads past the tensor and is zero-filled): the decode step of the KV-cache
+    path (M = batch), the CLAP projector (one frame per sample) and the MPT head at decode time."""
+    ops = _ops()
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(BF16)
+    b = (torch.randn(N, K, device="cuda") * 0.5).to(BF16)
+    ldn = (N + 63) // 64 * 64
+    buf = torch.zeros(M, ldn, device="cuda", dtype=BF16)
+    ops.gemm(a, b, out=buf, N=N)
+    assert _rel(buf[:, :N], a.float() @ b.float().t()) < 5e-3
+    assert buf[:, N:].abs().sum().item() == 0
+
+
 def test_gemm_bias_residual_and_fp32_out(gemm_mode):
     ops = _ops()
     torch.manual_seed(0)
