@@ -73,3 +73,41 @@ def test_pad_and_audio_token_surgery_matches_reference(tmp_path, tune):
         assert torch.equal(has_r[0], has_o[0])
         assert not any(p.requires_grad for p in mo.get_output_embeddings().parameters())
         assert all(p.requires_grad for p in mo.get_input_embeddings().parameters())
+
+
+def test_projector_initialisation_and_pretrained_load_match_reference(tmp_path):
+    """M2 (m2t/models/llamav2.py:60-93): nn.Linear(mm_hidden_size, hidden_size) with bias, created once, filled from the
+    `*mm_projector*` keys of a side file such as WrappedTrainer._save writes (other keys in the file are ignored)."""
+    import llark_b200.models.llamav2 as ours_mod
+    from test_reference_train_dropin_cpu import _tiny_checkpoint
+
+    ref_shims.install()
+    import m2t.models.llamav2 as ref_mod
+
+    ck = str(tmp_path / "tiny-llama-ckpt")
+    _tiny_checkpoint(ck, random.Random(0))
+    g = torch.Generator().manual_seed(5)
+    side = {"model.mm_projector.weight": torch.randn(256, 12, generator=g), "model.mm_projector.bias": torch.randn(256, generator=g),
+            "model.embed_tokens.weight": torch.randn(8, 256, generator=g)}
+    path = str(tmp_path / "mm_projector.bin")
+    torch.save(side, path)
+    out = {}
+    for name, mod in (("ref", ref_mod), ("ours", ours_mod)):
+        model = mod.WrappedLlamav2ForCausalLM.from_pretrained(ck, mm_hidden_size=12)
+        assert not hasattr(model.get_model(), "mm_projector")
+        res = model.get_model().initialize_adapter_modules(pretrain_mm_mlp_adapter=path, tune_mm_mlp_adapter=True, fsdp=None)
+        first = model.get_model().mm_projector
+        model.get_model().initialize_adapter_modules()                      # second call keeps the module
+        assert model.get_model().mm_projector is first
+        out[name] = (model, res)
+    (mr, rr), (mo, ro) = out["ref"], out["ours"]
+    assert sorted(rr) == sorted(ro) == ["audio_config"]
+    assert type(rr["audio_config"]).__name__ == type(ro["audio_config"]).__name__ == "AudioEncoderConfig"
+    # (upstream `audio_patch_token = str = ...` makes that one a class attribute; attribute access is what callers use)
+    for f in ("use_audio_start_end", "audio_start_token", "audio_end_token", "audio_patch_token"):
+        assert getattr(rr["audio_config"], f) == getattr(ro["audio_config"], f), f
+    assert mr.config.use_mm_proj is True and mo.config.use_mm_proj is True
+    for k in ("weight", "bias"):
+        a, b = getattr(mr.get_model().mm_projector, k).data, getattr(mo.get_model().mm_projector, k).data
+        assert torch.equal(a, b) and torch.equal(b, side["model.mm_projector." + k])
+    assert set(mr.state_dict()) == set(mo.state_dict())                     # same key names incl. model.mm_projector.*
