@@ -140,6 +140,12 @@ int llark_ln_bwd(const void* x, long long ldx, const void* w, const void* dy, lo
  * u * phi(u)); bf16, n a multiple of 8. */
 int llark_gelu_fwd(const void* u, void* h, long long n, cudaStream_t stream);
 int llark_gelu_bwd(const void* u, const void* dh, void* du, long long n, cudaStream_t stream);
+/* Skinny linear layer of the decode step: C[M,N] = A[M,K] . W[N,K]^T (+ bias[N]) (+ R[M,N]), 1 <= M <= 8, bf16, fp32
+ * accumulation; K and the leading dimensions (elements) multiples of 8. Streams W once (HBM-bound SIMT kernel; the tcgen05
+ * GEMM core would run 128-row tiles of padding). Same arithmetic contract as llark_gemm with these arguments
+ * (transformers LlamaDecoderLayer linears reached from m2t/models/llamav2.py:224 during generate, m2t/infer.py:146-152). */
+int llark_gemv(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, const void* bias,
+               const void* R, long long ldr, int M, int N, int K, cudaStream_t stream);
 /* Single-token decode step against a KV cache (transformers' cached LlamaAttention behind m2t/infer.py's
  * model.generate): q [B, n_heads*128] (RoPE applied), k_cache / v_cache [B, s_max, n_heads*128] bf16, lens int32 [B] =
  * valid cached positions per row including the new token (<= s_max <= 4096), out [B, n_heads*128]. */

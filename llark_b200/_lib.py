@@ -17,7 +17,7 @@ SYMBOLS = [
     "llark_last_cuda_error", "llark_gemm", "llark_gemm_ex", "llark_gemm_clear_cache", "llark_gemm_set_mode", "llark_gemm_get_mode", "llark_splice_scan", "llark_embed_splice_fwd",
     "llark_embed_splice_bwd", "llark_cast_f32_to_bf16", "llark_cast_bf16_to_f32", "llark_rmsnorm_fwd",
     "llark_rmsnorm_bwd_workspace", "llark_rmsnorm_bwd", "llark_rope", "llark_swiglu_fwd", "llark_swiglu_bwd",
-    "llark_attn_fwd", "llark_attn_decode", "llark_attn_alibi_fwd", "llark_attn_alibi_bwd", "llark_ln_fwd",
+    "llark_attn_fwd", "llark_attn_decode", "llark_gemv", "llark_attn_alibi_fwd", "llark_attn_alibi_bwd", "llark_ln_fwd",
     "llark_ln_bwd_workspace", "llark_ln_bwd", "llark_gelu_fwd", "llark_gelu_bwd", "llark_attn_bwd_workspace", "llark_attn_bwd", "llark_ce_fwd", "llark_ce_bwd",
     "llark_sumsq_workspace", "llark_grad_sumsq", "llark_adamw_step", "llark_comm_unique_id", "llark_comm_init",
     "llark_comm_destroy", "llark_grad_bucket_allreduce", "llark_jb_conv_down", "llark_jb_resblock",
@@ -76,6 +76,7 @@ def lib():
             "llark_swiglu_bwd": ([P, P, P, LL, I, P], I),
             "llark_attn_fwd": ([P, P, P, P, I, I, I, I, F, P], I),
             "llark_attn_decode": ([P, P, P, P, P, I, I, I, I, F, P], I),
+            "llark_gemv": ([P, LL, P, LL, P, LL, P, P, LL, I, I, I, P], I),
             "llark_attn_alibi_fwd": ([P, P, P, P, P, I, I, I, I, F, P], I),
             "llark_attn_alibi_bwd": ([P, P, P, P, P, P, P, I, I, I, I, F, P, P], I),
             "llark_ln_fwd": ([P, LL, P, P, LL, P, P, LL, I, F, P], I),

@@ -425,6 +425,9 @@ class LlamaEngine:
         cos_t, sin_t = cos[t:], sin[t:]  # row 0 of these views is position t: with S = 1 every row reads it
         cache.lens.fill_(t + 1)
         rstd = torch.empty(B, device=dev, dtype=torch.float32)
+        # up to 8 rows the linears are weight-streaming GEMVs (csrc/gemv.cu); LLARK_DECODE_GEMV=0 keeps the GEMM core
+        skinny = B <= 8 and os.environ.get("LLARK_DECODE_GEMV", "1") != "0"
+        lin = ops.gemv if skinny else ops.gemm
         for l in range(L):
             pfx = f"model.layers.{l}."
             Wqkv = flat.pview(pfx + "self_attn.q_proj.weight", (3 * H, H), span=3)
@@ -432,23 +435,23 @@ class LlamaEngine:
             Wgu = flat.pview(pfx + "mlp.gate_proj.weight", (2 * I, H), span=2)
             Wd = flat.pview(pfx + "mlp.down_proj.weight", (H, I))
             xn1 = ops.rmsnorm_fwd(x, flat.pview(pfx + "input_layernorm.weight"), eps, rstd=rstd)
-            if self.fuse_epilogues and D == 128:
+            if self.fuse_epilogues and D == 128 and not skinny:
                 qkv = ops.gemm(xn1, Wqkv, rope=(cos_t, sin_t, 1, 2 * H))
             else:
-                qkv = ops.gemm(xn1, Wqkv)
+                qkv = lin(xn1, Wqkv)
                 ops.rope_(qkv, cos_t, sin_t, 1, NH, D)
             cache.k[l][:, t].copy_(qkv[:, H:2 * H])
             cache.v[l][:, t].copy_(qkv[:, 2 * H:])
             attn = ops.attn_decode(qkv[:, :H].contiguous(), cache.k[l], cache.v[l], cache.lens, NH, D)
-            x_mid = ops.gemm(attn, Wo, residual=x)
+            x_mid = lin(attn, Wo, residual=x)
             xn2 = ops.rmsnorm_fwd(x_mid, flat.pview(pfx + "post_attention_layernorm.weight"), eps, rstd=rstd)
-            gu = ops.gemm(xn2, Wgu)
+            gu = lin(xn2, Wgu)
             act = ops.swiglu_fwd(gu)
-            x = ops.gemm(act, Wd, residual=x_mid)
+            x = lin(act, Wd, residual=x_mid)
         hn = ops.rmsnorm_fwd(x, flat.pview("model.norm.weight"), eps, rstd=rstd)
         ldv = (V + 63) // 64 * 64
         logits_buf = torch.empty((B, ldv), device=dev, dtype=BF16)
-        ops.gemm(hn, flat.pview("lm_head.weight", (V, H)), out=logits_buf, N=V)
+        lin(hn, flat.pview("lm_head.weight", (V, H)), out=logits_buf, N=V)
         cache.length = t + 1
         return logits_buf.view(B, 1, ldv)[:, :, :V]
 

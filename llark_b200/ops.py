@@ -198,6 +198,17 @@ def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, 
     return dqkv
 
 
+def gemv(x, w, bias=None, residual=None, out=None, N=None):
+    """y[M, N] = x[M, K] @ w[N, K]^T (+ bias) (+ residual) for M <= 8 rows: the weight-streaming kernel of the decode step
+    (STAGED, see csrc/gemv.cu). `out` may be wider than N (padded logits buffer)."""
+    M, K = x.shape
+    N = int(N) if N is not None else w.shape[0]
+    out = out if out is not None else torch.empty((M, N), device=x.device, dtype=BF16)
+    check(lib().llark_gemv(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), _p(bias), _p(residual),
+                           residual.stride(0) if residual is not None else 0, M, N, K, _stream()), "gemv")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ MPT variant (staged)
 def attn_alibi_fwd(qkv, key_mask, B, S, n_heads, head_dim, slopes, out=None, lse=None):
     out = out if out is not None else torch.empty((B * S, n_heads * head_dim), device=qkv.device, dtype=BF16)

@@ -384,6 +384,20 @@ def jb_pool(acts, T_valid, frame):
 
 
 # ------------------------------------------------------------------------------------------------ MPT variant (staged ops)
+def gemv(x, w, bias=None, residual=None, out=None, N=None):
+    N = int(N) if N is not None else w.shape[0]
+    y = x.float() @ w[:N].float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if residual is not None:
+        y = y + residual.float()
+    y = y.to(BF16)
+    if out is not None:
+        out[:, :N].copy_(y)
+        return out
+    return y
+
+
 def ln_fwd(x, w, eps, mean=None, rstd=None, out=None, out_dtype=BF16):
     """Bias-free LayerNorm over the last dim of a (possibly strided) [rows, W] view; fp32 statistics."""
     xf = x.float()

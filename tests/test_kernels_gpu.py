@@ -80,6 +80,33 @@ def test_gemm_very_few_rows(M, N, K, gemm_mode):
     assert buf[:, N:].abs().sum().item() == 0
 
 
+@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
+                    reason="staged kernel that has not run on a B200 yet (set LLARK_STAGED=1)")
+@pytest.mark.parametrize("M,N,K", [(1, 12288, 4096), (1, 4096, 11008), (3, 22016, 4096), (8, 32004, 4096), (2, 72, 136)])
+def test_gemv_decode_linear(M, N, K):
+    """llark_gemv (weight-streaming linear of the decode step) against fp32 math and against the GEMM core it replaces."""
+    ops = _ops()
+    torch.manual_seed(M * 5 + N + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(BF16)
+    w = (torch.randn(N, K, device="cuda") * 0.5).to(BF16)
+    bias = torch.randn(N, device="cuda").to(BF16)
+    res = torch.randn(M, N, device="cuda").to(BF16)
+    ref = x.float() @ w.float().t()
+    assert _rel(ops.gemv(x, w), ref) < 4e-3
+    assert _rel(ops.gemv(x, w, bias=bias, residual=res), ref + bias.float() + res.float()) < 4e-3
+    ldn = (N + 63) // 64 * 64
+    buf = torch.zeros(M, ldn, device="cuda", dtype=BF16)
+    ops.gemv(x, w, out=buf, N=N)
+    assert _rel(buf[:, :N], ref) < 4e-3 and buf[:, N:].abs().sum().item() == 0
+    # strided input rows (a column slice of a wider buffer), as qkv[:, :H] would be
+    wide = torch.zeros(M, K + 64, device="cuda", dtype=BF16)
+    wide[:, :K] = x
+    assert torch.equal(ops.gemv(wide[:, :K], w), ops.gemv(x, w))
+    if K % 64 == 0 and N % 8 == 0:
+        g = ops.gemm(x, w)                                  # both round fp32 sums once: equal up to summation order
+        assert _rel(ops.gemv(x, w), g.float()) < 4e-3
+
+
 def test_gemm_bias_residual_and_fp32_out(gemm_mode):
     ops = _ops()
     torch.manual_seed(0)
