@@ -334,7 +334,7 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, out_dtype=torch.float32, out=None):
     return _F.layer_norm(x.float(), x.shape[-1:], gamma, beta, eps).to(out_dtype)
 
 
-def jb_embed_tokens(codes, emb, y_cond, pos_emb, x_cond, out=None):
+def jb_embed_tokens(codes, emb, y_cond, pos_emb, x_cond):
     N, T = codes.shape
     x = emb[codes]
     x = torch.roll(x, 1, dims=1)

@@ -246,3 +246,30 @@ def test_trainer_checkpoint_resume_is_exact(cpu_engine, monkeypatch, tmp_path):
     assert resumed.state["global_step"] == 4 and len(resumed.state["log_history"]) == 4
     assert resumed.optimizer.step_count == 4
     assert torch.equal(resumed.model.engine.flat.params, ref)
+
+
+def test_stand_in_ops_track_the_real_signatures():
+    """tests/cpu_ops.py is only a valid stand-in while every function it offers exists in llark_b200.ops with the same
+    leading parameters (the real wrappers may add optional output buffers; gemm takes its options as keywords)."""
+    import inspect
+
+    import cpu_ops
+    import llark_b200.ops as real
+
+    for name, fn in vars(cpu_ops).items():
+        if name.startswith("_") or not inspect.isfunction(fn) or fn.__module__ != "cpu_ops" or name == "lib":
+            continue
+        assert hasattr(real, name), f"stand-in op {name} does not exist in llark_b200.ops"
+        want = list(inspect.signature(getattr(real, name)).parameters)
+        have = [p for p in inspect.signature(fn).parameters if p != "kw"]
+        assert have == want[: len(have)], (name, have, want)
+    offered = {n for n, f in vars(cpu_ops).items() if inspect.isfunction(f) and f.__module__ == "cpu_ops"}
+    import ast
+
+    for path in ("llark_b200/engine.py", "llark_b200/engine_mpt.py", "llark_b200/optim.py", "llark_b200/jukebox/model.py"):
+        src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), path)).read()
+        used = {n.attr for n in ast.walk(ast.parse(src)) if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name)
+                and n.value.id == "ops"}
+        used -= {"GEMM_PROFILE"}
+        assert used <= offered, (path, sorted(used - offered))
+
