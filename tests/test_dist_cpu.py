@@ -63,6 +63,54 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/llark_b200.h against the argtypes / restype llark_b200/_lib.py binds: same arity, and
+    each parameter in the same class (pointer / stream / comm handle -> void*, long long, int, float). Catches ABI drift
+    of entry points that cannot be called in the CPU suite."""
+    import ctypes
+    import re
+
+    sys.path.insert(0, ROOT)
+    from llark_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "llark_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(llark_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)
+    assert len(protos) >= 40
+
+    def classify(decl):
+        decl = decl.strip()
+        if decl in ("", "void"):
+            return None
+        if "*" in decl or re.search(r"\b(cudaStream_t|ncclComm_t|LlarkComm)\b", decl):
+            return ctypes.c_void_p
+        if re.search(r"\blong\s+long\b|\bsize_t\b|\bint64_t\b", decl):
+            return ctypes.c_longlong
+        if re.search(r"\bfloat\b", decl):
+            return ctypes.c_float
+        if re.search(r"\bdouble\b", decl):
+            return ctypes.c_double
+        if re.search(r"\b(int|unsigned)\b", decl):
+            return ctypes.c_int
+        raise AssertionError(f"unclassified parameter {decl!r}")
+
+    lib = _lib.lib()
+    seen = set()
+    for ret, name, args in protos:
+        seen.add(name)
+        want = [c for c in (classify(a) for a in args.split(",")) if c is not None]
+        fn = getattr(lib, name)
+        have = list(fn.argtypes or [])
+        assert len(have) == len(want), (name, len(have), len(want))
+        for i, (h, w) in enumerate(zip(have, want)):
+            assert h is w, (name, i, h, w)
+        ret = ret.replace("extern", "").strip()
+        want_ret = None if ret == "void" else classify(ret)
+        assert fn.restype is want_ret, (name, fn.restype, want_ret)
+    assert seen == set(_lib.SYMBOLS)
+
+
 def test_no_cpu_fallback():
     """Calling an op without CUDA tensors must fail loudly (the product path never routes through the oracle)."""
     import pytest
