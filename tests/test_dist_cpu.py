@@ -111,6 +111,32 @@ def test_ctypes_signatures_match_the_header_prototypes():
     assert seen == set(_lib.SYMBOLS)
 
 
+def test_every_call_site_passes_as_many_arguments_as_the_binding_declares():
+    """Static arity check of every `lib().llark_*(...)` call in the package against the bound argtypes: ctypes would only
+    complain at call time, which for GPU entry points is never in the CPU suite."""
+    import ast
+    import glob
+
+    sys.path.insert(0, ROOT)
+    from llark_b200 import _lib
+
+    lib = _lib.lib()
+    checked = 0
+    files = glob.glob(os.path.join(ROOT, "llark_b200", "**", "*.py"), recursive=True)
+    files += [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for path in files:
+        for node in ast.walk(ast.parse(open(path).read())):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)
+                    and node.func.attr.startswith("llark_")):
+                continue
+            name = node.func.attr
+            assert not node.keywords and not any(isinstance(a, ast.Starred) for a in node.args), (path, node.lineno)
+            fn = getattr(lib, name)
+            assert len(node.args) == len(fn.argtypes or []), (path, node.lineno, name, len(node.args))
+            checked += 1
+    assert checked >= 45
+
+
 def test_no_cpu_fallback():
     """Calling an op without CUDA tensors must fail loudly (the product path never routes through the oracle)."""
     import pytest
