@@ -164,7 +164,8 @@ class LlamaEngine:
         self.grad_ready_hook = None
         self.flags = None  # device int32[1]: splice validation bits (see llark_splice_scan)
         self.launches = 0  # kernels launched by the last forward(+backward): bench.py's gpu_launches
-        self.comm_chunk_layers = 4
+        # layers per all-reduce slice (1.6 GB at 4 for the 7B model); the last slice is the exposed one
+        self.comm_chunk_layers = max(1, int(os.environ.get("LLARK_COMM_CHUNK_LAYERS", "4")))
         # RoPE and SwiGLU-backward fused into GEMM epilogues (llark_gemm_ex); LLARK_FUSE_EPILOGUES=0 keeps the
         # separate llark_rope / llark_swiglu_bwd kernels (same results bit for bit)
         self.fuse_epilogues = os.environ.get("LLARK_FUSE_EPILOGUES", "1") != "0"
