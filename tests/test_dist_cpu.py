@@ -149,6 +149,20 @@ def test_no_cpu_fallback():
     src = open(os.path.join(ROOT, "llark_b200", "engine.py")).read() + open(
         os.path.join(ROOT, "llark_b200", "ops.py")).read()
     assert "oracle" not in src
+    # no module of the package imports the oracle, the tests or the CPU stand-in -- not even lazily inside a function
+    import ast
+    import glob
+
+    for path in glob.glob(os.path.join(ROOT, "llark_b200", "**", "*.py"), recursive=True):
+        for node in ast.walk(ast.parse(open(path).read())):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for n in names:
+                root = n.split(".")[0]
+                assert root not in ("oracle", "tests", "cpu_ops"), (path, node.lineno, n)
 
 
 def test_cosine_schedule_matches_hf_formula():
