@@ -216,6 +216,15 @@ class MPTEngine(LlamaEngine):
             wgrad(pfx + "attn.Wqkv.weight", dqkv_raw, a, (3 * d, d))
             ops.ln_bwd(x, flat.pview(pfx + "norm_1.weight"), da, mu1, rs1, dx_mid, dx,
                        flat.gview(pfx + "norm_1.weight"), acc)
+            if self.grad_ready_hook is not None and l % self.comm_chunk_layers == 0:
+                # blocks [l, hi) are final and contiguous in the bucket: their all-reduce can start now (the tied table,
+                # final norm and projector are reduced by the optimizer's step())
+                lo_off = flat.offsets[f"transformer.blocks.{l}.norm_1.weight"][0]
+                hi_l = min(l + self.comm_chunk_layers, L)
+                hi_off = (flat.offsets[f"transformer.blocks.{hi_l}.norm_1.weight"][0] if hi_l < L
+                          else flat.offsets["transformer.norm_f.weight"][0])
+                if lo_off < flat.n_train and hi_off <= flat.n_train and hi_off > lo_off:
+                    self.grad_ready_hook(lo_off, hi_off)
 
         # splice + projector + embedding scatter into the (already written) tied-table gradient
         g_table = flat.gview("transformer.wte.weight", (V, d))

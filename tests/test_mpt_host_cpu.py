@@ -114,3 +114,35 @@ def test_mpt_config_envelope_and_errors(cpu_mpt):
 
     assert torch.allclose(alibi_slopes(8), torch.tensor([2.0 ** -(i + 1) for i in range(8)]))
     assert torch.allclose(alibi_slopes(6), mo.gen_slopes(6))
+
+
+def test_mpt_backward_announces_block_gradients_for_the_overlapped_allreduce(cpu_mpt):
+    """Data-parallel overlap: during backward the engine hands contiguous, final slices of the flat gradient
+    bucket to `grad_ready_hook` in reverse block order; together they cover exactly the blocks' parameters, and a slice's
+    contents do not change afterwards (the optimizer all-reduces it on a side stream meanwhile)."""
+    from oracle import mpt_oracle as mo
+
+    cfg = mo.MPTCfg(d_model=256, n_heads=2, n_layers=5)
+    model = _build(cfg, mo.init_params(cfg, seed=0))
+    batch = mo.make_batch(cfg, B=2, S=40, F_frames=1, seed=0)
+    eng = model.engine
+    eng.comm_chunk_layers = 2
+    calls = []
+
+    def hook(lo, hi):
+        calls.append((lo, hi, eng.flat.grads[lo:hi].clone()))
+
+    eng.grad_ready_hook = hook
+    model(**batch).loss.backward()
+    flat = eng.flat
+    spans = [(lo, hi) for lo, hi, _ in calls]
+    assert spans == sorted(spans, reverse=True) and len(spans) == 3              # blocks {4}, {2,3}, {0,1}
+    first = flat.offsets["transformer.blocks.0.norm_1.weight"][0]
+    last = flat.offsets["transformer.norm_f.weight"][0]
+    assert spans[-1][0] == first and spans[0][1] == last
+    assert all(spans[i][0] == spans[i + 1][1] for i in range(len(spans) - 1))
+    for lo, hi, snap in calls:
+        assert torch.equal(flat.grads[lo:hi], snap)                              # final when announced
+    wte = flat.offsets["transformer.wte.weight"][0]
+    assert not (first <= wte < last)                                             # the tied table is left to step()
+
