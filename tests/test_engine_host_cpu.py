@@ -248,6 +248,34 @@ def test_trainer_checkpoint_resume_is_exact(cpu_engine, monkeypatch, tmp_path):
     assert torch.equal(resumed.model.engine.flat.params, ref)
 
 
+def test_backward_announces_final_layer_gradients_in_reverse_order(cpu_engine):
+    """The overlap hook of the data-parallel step: slices handed to `grad_ready_hook` are contiguous, arrive in reverse
+    layer order, cover exactly the decoder layers, and do not change after they were announced (also under accumulation,
+    where the second backward adds into the bucket before announcing)."""
+    from oracle import llama_oracle as lo
+
+    cfg = lo.LlamaCfg(num_layers=5)
+    model = _build(cfg, lo.init_params(cfg, seed=0))
+    for p in model.get_output_embeddings().parameters():
+        p.requires_grad = False
+    batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=0)
+    eng = model.engine
+    eng.comm_chunk_layers = 2
+    calls = []
+    eng.grad_ready_hook = lambda lo_, hi_: calls.append((lo_, hi_, eng.flat.grads[lo_:hi_].clone()))
+    for rounds in (1, 2):                       # second pass accumulates into the live bucket
+        calls.clear()
+        model(**batch).loss.backward()
+        flat = eng.flat
+        spans = [(a, b) for a, b, _ in calls]
+        assert spans == sorted(spans, reverse=True) and len(spans) == 3
+        assert spans[-1][0] == flat.offsets["model.layers.0.self_attn.q_proj.weight"][0]
+        assert spans[0][1] == flat.offsets["model.norm.weight"][0]
+        assert all(spans[i][0] == spans[i + 1][1] for i in range(len(spans) - 1))
+        for a, b, snap in calls:
+            assert torch.equal(flat.grads[a:b], snap)
+
+
 def test_stand_in_ops_track_the_real_signatures():
     """tests/cpu_ops.py is only a valid stand-in while every function it offers exists in llark_b200.ops with the same
     leading parameters (the real wrappers may add optional output buffers; gemm takes its options as keywords)."""
