@@ -1,4 +1,4 @@
-# Build the llark_b200 C-ABI library (sm_100a only) and the oracle's native pieces.
+# Build the llark_b200 C-ABI library (sm_100a only).
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v
@@ -12,13 +12,12 @@ build/%.o: llark_b200/csrc/%.cu llark_b200/csrc/common.cuh include/llark_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
+# the ALiBi instantiation #includes the attention source: rebuild it when that changes
+build/attention_tc_alibi.o: llark_b200/csrc/attention_tc.cu
+
 $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lnccl
 
-tools: build/gemm_check
-build/gemm_check: tools/gemm_check.cu $(LIB)
-	$(NVCC) $(ARCH) -std=c++17 -O2 -o $@ tools/gemm_check.cu -Lllark_b200 -lllark_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../llark_b200'
-
 clean:
 	rm -rf build $(LIB)
-.PHONY: all clean tools
+.PHONY: all clean
