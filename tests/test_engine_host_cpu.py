@@ -276,6 +276,55 @@ def test_backward_announces_final_layer_gradients_in_reverse_order(cpu_engine):
             assert torch.equal(flat.grads[a:b], snap)
 
 
+def test_frozen_backbone_projector_only_training(cpu_engine, monkeypatch):
+    """`--freeze_backbone True --tune_mm_mlp_adapter True` (m2t/train.py:79-80,143-152 + llamav2.py:408-415): only the
+    projector and the embedding table are trainable. The backward still runs dgrad through every layer to reach the
+    projector, writes no weight gradient for frozen tensors, and the fused optimizer steps a bucket that holds just the
+    two trainable tensors."""
+    import cpu_ops
+    import llark_b200.optim as optim
+    from oracle import llama_oracle as lo
+
+    monkeypatch.setattr(optim, "ops", cpu_ops)
+    cfg = lo.LlamaCfg()
+    params = lo.init_params(cfg, seed=0)
+    batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=1)
+    model = _build(cfg, params)
+    model.requires_grad_(False)
+    for p in model.get_model().mm_projector.parameters():
+        p.requires_grad = True
+    for p in model.get_input_embeddings().parameters():
+        p.requires_grad = True
+    model.get_model().orig_embeds_params = [model.get_input_embeddings().weight.data.clone()]
+    opt = optim.LlarkAdamW(model, lr=1e-2)
+    flat = model.engine.flat
+    trainable = {"model.embed_tokens.weight", "model.mm_projector.weight", "model.mm_projector.bias"}
+    assert flat.n_train <= sum(p.numel() for n, p in model.named_parameters() if n in trainable) + 3 * 128
+    hooked = []
+    model.engine.grad_ready_hook = lambda a, b: hooked.append((a, b))
+    out = model(**batch)
+    out.loss.backward()
+    assert hooked == []                                           # no decoder layer owns a slice of the trainable bucket
+    pb = {k: v.to(BF16) for k, v in params.items()}
+    loss_o, _, grads_o = lo.forward_backward(pb, cfg, batch)
+    assert abs(out.loss.item() - loss_o.item()) < 3e-3 * loss_o.item()
+    named = dict(model.named_parameters())
+    for n, p in named.items():
+        if n in trainable:
+            ref = grads_o[n].float()
+            assert ((p.grad.float() - ref).norm() / (ref.norm() + 1e-30)).item() < 6e-2, n
+        else:
+            assert p.grad is None, n
+    l0 = out.loss.item()
+    before = named["model.layers.0.mlp.down_proj.weight"].detach().clone()
+    for _ in range(3):
+        opt.step()
+        model(**batch).loss.backward()
+    with torch.no_grad():
+        assert model(**batch).loss.item() < l0
+    assert torch.equal(named["model.layers.0.mlp.down_proj.weight"], before)          # frozen weights never move
+
+
 def test_stand_in_ops_track_the_real_signatures():
     """tests/cpu_ops.py is only a valid stand-in while every function it offers exists in llark_b200.ops with the same
     leading parameters (the real wrappers may add optional output buffers; gemm takes its options as keywords)."""

@@ -308,3 +308,35 @@ def test_wrapped_trainer_follows_the_reference_trajectory_on_gpu(tmp_path):
     model = build_model(cfg, lo.init_params(cfg, seed=gold_t["seed"]), detach_text=True)
     trainer = run_trajectory(model, gold_t, tmp_path)
     check_against_reference(trainer, model, gold_t, loss_tol=1e-2, delta_tol=0.05, cos_min=0.98)
+
+
+@STAGED
+def test_frozen_backbone_projector_only_training_on_gpu(gold):
+    """GPU twin of tests/test_engine_host_cpu.py::test_frozen_backbone_projector_only_training (--freeze_backbone True):
+    null weight-gradient pointers for every decoder tensor, dgrad through all layers, a bucket with two trainable tensors."""
+    from oracle import llama_oracle as lo
+    from llark_b200.optim import LlarkAdamW
+
+    cfg = lo.LlamaCfg(**gold["cfg"])
+    params = lo.init_params(cfg, seed=0)
+    batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=1)
+    model = build_model(cfg, params, detach_text=True)
+    model.requires_grad_(False)
+    for p in model.get_model().mm_projector.parameters():
+        p.requires_grad = True
+    for p in model.get_input_embeddings().parameters():
+        p.requires_grad = True
+    opt = LlarkAdamW(model, lr=1e-2)
+    out = model(**_to_cuda(batch))
+    out.loss.backward()
+    _, _, grads_o = lo.forward_backward({k: v.to(torch.bfloat16) for k, v in params.items()}, cfg, batch)
+    named = dict(model.named_parameters())
+    for n in ("model.mm_projector.weight", "model.mm_projector.bias", "model.embed_tokens.weight"):
+        assert _rel(named[n].grad.float(), grads_o[n].float()) < 6e-2, n
+    assert all(p.grad is None for n, p in named.items() if "layers" in n or n in ("model.norm.weight", "lm_head.weight"))
+    l0 = out.loss.item()
+    for _ in range(3):
+        opt.step()
+        model(**_to_cuda(batch)).loss.backward()
+    with torch.no_grad():
+        assert model(**_to_cuda(batch)).loss.item() < l0

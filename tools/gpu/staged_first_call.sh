@@ -10,7 +10,7 @@
 mkdir -p gpurun_out
 TAG=${1:-r2a}
 ( LLARK_STAGED=1 timeout 600 python -m pytest tests/test_mpt_gpu.py tests/test_kernels_gpu.py tests/test_model_gpu.py -m gpu -q \
-    -k "mpt or layernorm_forward or exact_gelu or alibi or decode_step or kv_cache or long_sequences or recompute or trajectory or very_few_rows or gemv" 2>&1 | tail -40 ) > gpurun_out/${TAG}_staged_pytest.txt 2>&1
+    -k "mpt or layernorm_forward or exact_gelu or alibi or decode_step or kv_cache or long_sequences or recompute or trajectory or very_few_rows or gemv or frozen_backbone" 2>&1 | tail -40 ) > gpurun_out/${TAG}_staged_pytest.txt 2>&1
 tail -3 gpurun_out/${TAG}_staged_pytest.txt
 ( LLARK_STAGED=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_mpt_gpu.py -m gpu -q -x \
     -k "layernorm_forward or exact_gelu and not 2457600 or alibi and 128" 2>&1 | tail -30 ) > gpurun_out/${TAG}_staged_memcheck.txt 2>&1
