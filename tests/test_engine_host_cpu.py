@@ -325,6 +325,36 @@ def test_frozen_backbone_projector_only_training(cpu_engine, monkeypatch):
     assert torch.equal(named["model.layers.0.mlp.down_proj.weight"], before)          # frozen weights never move
 
 
+def test_frozen_projector_backbone_training(cpu_engine, monkeypatch):
+    """`--freeze_mm_mlp_adapter True` (m2t/train.py:154-158): the projector gets no gradient, everything else trains."""
+    import cpu_ops
+    import llark_b200.optim as optim
+    from oracle import llama_oracle as lo
+
+    monkeypatch.setattr(optim, "ops", cpu_ops)
+    cfg = lo.LlamaCfg()
+    params = lo.init_params(cfg, seed=0)
+    batch = lo.make_batch(cfg, B=2, S=48, F_frames=5, seed=2)
+    model = _build(cfg, params)
+    for p in model.get_output_embeddings().parameters():
+        p.requires_grad = False
+    for p in model.get_model().mm_projector.parameters():
+        p.requires_grad = False
+    model.get_model().orig_embeds_params = [model.get_input_embeddings().weight.data.clone()]
+    opt = optim.LlarkAdamW(model, lr=1e-3)
+    out = model(**batch)
+    out.loss.backward()
+    _, _, grads_o = lo.forward_backward({k: v.to(BF16) for k, v in params.items()}, cfg, batch)
+    named = dict(model.named_parameters())
+    assert named["model.mm_projector.weight"].grad is None and named["model.mm_projector.bias"].grad is None
+    for n in ("model.layers.0.self_attn.q_proj.weight", "model.layers.1.mlp.gate_proj.weight", "model.norm.weight"):
+        ref = grads_o[n].float()
+        assert ((named[n].grad.float() - ref).norm() / ref.norm()).item() < 6e-2, n
+    proj_before = named["model.mm_projector.weight"].detach().clone()
+    opt.step()
+    assert torch.equal(named["model.mm_projector.weight"], proj_before)
+
+
 def test_stand_in_ops_track_the_real_signatures():
     """tests/cpu_ops.py is only a valid stand-in while every function it offers exists in llark_b200.ops with the same
     leading parameters (the real wrappers may add optional output buffers; gemm takes its options as keywords)."""
