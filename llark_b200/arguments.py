@@ -84,7 +84,9 @@ class TrainingArguments:
     save_strategy: str = _opt("steps")
     save_steps: int = _opt(500)
     save_total_limit: Optional[int] = _opt(None)
-    eval_strategy: str = _opt("no")
+    eval_strategy: str = _opt("no", "'steps' evaluates every --eval_steps optimizer steps when --eval_data_path is given")
+    eval_steps: Optional[int] = _opt(None, "defaults to --logging_steps, as in transformers")
+    per_device_eval_batch_size: int = _opt(8)
     bf16: bool = _opt(False)
     fp16: bool = _opt(False)
     tf32: Optional[bool] = _opt(None, "accepted; the Llama path computes in bf16 on tcgen05 either way")

@@ -95,6 +95,45 @@ class WrappedTrainer:
             for batch in loader:
                 yield batch
 
+    @torch.no_grad()
+    def evaluate(self, eval_dataset=None, max_batches=None):
+        """Mean loss over the evaluation set, as transformers.Trainer.evaluate reports `eval_loss` (mean of the per-batch
+        mean losses; the reference's make_data_module returns `eval_dataset`, m2t/data_modules.py:707-717). Every rank
+        evaluates the shards it was dealt; with more than one rank the per-rank means are averaged."""
+        dataset = eval_dataset if eval_dataset is not None else self.eval_dataset
+        if dataset is None:
+            raise ValueError("no evaluation dataset: pass --eval_data_path (or eval_dataset=)")
+        bs = self._arg("per_device_eval_batch_size", None) or self._arg("per_device_train_batch_size", 2)
+        loader = torch.utils.data.DataLoader(dataset, batch_size=bs, collate_fn=self.data_collator,
+                                             num_workers=self._arg("dataloader_num_workers", 0), pin_memory=True)
+        dev = next(self.model.parameters()).device
+        was_training = self.model.training
+        self.model.eval()
+        total, count = torch.zeros((), device=dev, dtype=torch.float32), 0
+        try:
+            for i, batch in enumerate(loader):
+                if max_batches is not None and i >= max_batches:
+                    break
+                batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else
+                             [t.to(dev, non_blocking=True) for t in v]) for k, v in batch.items()}
+                total += self.model(**batch).loss.float()
+                count += 1
+        finally:
+            self.model.train(was_training)
+        self.model.check_audio_token_errors()
+        mean = (total / max(count, 1)).item()
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([mean], device=dev)
+            dist.all_reduce(t)
+            mean = (t / world).item()
+        metrics = {"eval_loss": mean, "eval_batches": count, "step": self.state["global_step"]}
+        self.state["log_history"].append(metrics)
+        logging.warning(json.dumps(metrics))
+        return metrics
+
     def train(self, resume_from_checkpoint=None):
         max_steps = self._arg("max_steps", -1)
         if max_steps is None or max_steps <= 0:
@@ -131,6 +170,10 @@ class WrappedTrainer:
                          "grad_norm": self.optimizer.grad_norm().item(), "elapsed_s": time.time() - t0}
                 self.state["log_history"].append(entry)
                 logging.warning(json.dumps(entry))
+            eval_steps = self._arg("eval_steps", None) or self._arg("logging_steps", 1)
+            if (self._arg("eval_strategy", self._arg("evaluation_strategy", "no")) == "steps" and self.eval_dataset is not None
+                    and self.state["global_step"] % max(1, eval_steps) == 0):
+                self.evaluate(max_batches=self._arg("eval_max_batches", None))
             save_steps = self._arg("save_steps", 0)
             if save_steps and self.state["global_step"] % save_steps == 0 and self._is_main():
                 ckpt = os.path.join(self._arg("output_dir", "."), f"checkpoint-{self.state['global_step']}")

@@ -90,3 +90,47 @@ def test_own_train_entry_point_runs_and_resumes(tmp_path, monkeypatch):
     assert {"checkpoint-2.bin", "checkpoint-4.bin", "checkpoint-6.bin"} <= set(os.listdir(os.path.join(out_dir, "mm_projector")))
     steps = [h["step"] for h in again.state["log_history"]]
     assert again.state["global_step"] == 6 and steps[-2:] == [5, 6] and again.optimizer.step_count == 6
+
+
+def test_periodic_evaluation(tmp_path, monkeypatch):
+    """--evaluation_strategy steps --eval_steps 2 with an eval shard: `eval_loss` entries appear in the log at steps 2 and
+    4, evaluation leaves parameters and the gradient bucket alone, and trainer.evaluate() can be called on its own."""
+    import cpu_ops
+    import llark_b200.engine as eng
+    import llark_b200.optim as optim
+    import llark_b200.train as entry
+    from test_reference_train_dropin_cpu import _shard, _tiny_checkpoint
+
+    monkeypatch.setattr(eng, "ops", cpu_ops)
+    monkeypatch.setattr(optim, "ops", cpu_ops)
+
+    def ensure_packed(self):
+        named = self._named()
+        if self.flat is None or not self.flat.is_current(named):
+            self.flat = eng.FlatBuckets(named, named[0][1].device)
+        return self.flat
+
+    monkeypatch.setattr(eng.LlamaEngine, "ensure_packed", ensure_packed)
+    rng = random.Random(0)
+    ck = str(tmp_path / "tiny-llama-ckpt")
+    _tiny_checkpoint(ck, rng)
+    train_shard, eval_shard = str(tmp_path / "train-000000.tar"), str(tmp_path / "eval-000000.tar")
+    _shard(train_shard, rng)
+    _shard(eval_shard, rng, n=3)
+    argv = ["--model_name_or_path", ck, "--output_dir", str(tmp_path / "out"), "--train_data_path", train_shard,
+            "--eval_data_path", eval_shard, "--mm_hidden_size", "12", "--tune_mm_mlp_adapter", "True",
+            "--mm_use_audio_start_end", "--bf16", "True", "--use_cpu", "True", "--max_steps", "4",
+            "--per_device_train_batch_size", "2", "--per_device_eval_batch_size", "2", "--learning_rate", "1e-3",
+            "--lr_scheduler_type", "cosine", "--logging_steps", "1", "--save_strategy", "no",
+            "--evaluation_strategy", "steps", "--eval_steps", "2"]
+    trainer = entry.main(argv)["trainer"]
+    evals = [h for h in trainer.state["log_history"] if "eval_loss" in h]
+    assert [h["step"] for h in evals] == [2, 4] and all(h["eval_batches"] == 2 for h in evals)   # 3 samples, batch 2
+    assert all(0 < h["eval_loss"] < 20 for h in evals) and evals[1]["eval_loss"] < evals[0]["eval_loss"] + 0.5
+    flat = trainer.model.engine.flat
+    before, grads = flat.params.clone(), flat.grads.clone()
+    again = trainer.evaluate()
+    assert torch.equal(flat.params, before) and torch.equal(flat.grads, grads)
+    # (the audio block goes before or after the question at random per pass, m2t/data_modules.py:328-329: not bit-equal)
+    assert abs(again["eval_loss"] - evals[1]["eval_loss"]) < 0.1 and trainer.model.training
+
