@@ -117,13 +117,12 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         **kwargs,
     ):
         """Same signature and return value as m2t/models/llamav2.py:259-337. Training / scoring / cache-less
-        generation (`generate` below). KV-cache decoding (past_key_values / use_cache=True) is the remaining part of
-        SURVEY §8(f) row 2."""
+        generation. `past_key_values` / `use_cache=True` run the KV-cache path (prefill + one-token decode steps,
+        SURVEY §8(f) row 2; verified on a B200 against the cache-less loop, tests/test_model_gpu.py)."""
         if past_key_values is not None or use_cache:
-            if os.environ.get("LLARK_KV_CACHE") != "1":
-                raise NotImplementedError("KV-cache decoding is staged behind LLARK_KV_CACHE=1 until it has run on a "
-                                          "B200 (SURVEY §8(f).2); WrappedLlamav2ForCausalLM.generate decodes without "
-                                          "a cache")
+            if os.environ.get("LLARK_KV_CACHE", "1") == "0":
+                raise NotImplementedError("KV-cache decoding is switched off (LLARK_KV_CACHE=0): generate() then runs "
+                                          "one full forward per token")
             return self._forward_cached(input_ids, attention_mask, past_key_values, labels, return_dict,
                                         audio_encodings)
         if position_ids is not None:
@@ -189,15 +188,15 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
                  max_length=None, do_sample=None, num_beams=None, eos_token_id=None, pad_token_id=None, **kwargs):
         """`model.generate(input_ids=, audio_encodings=, stopping_criteria=[...], max_new_tokens=...)` as called at
         m2t/infer.py:146-152 (and scripts/inference/*.py): greedy decoding of one prompt, returns the full sequences
-        [B, prompt + new] like GenerationMixin. Sampling / beam search are not built. No KV cache yet: each step is a
-        full forward over the sequence so far (llark_b200/generate.py); extra keyword arguments the reference passes
+        [B, prompt + new] like GenerationMixin. Sampling / beam search are not built. The prompt is prefilled once into a KV cache
+        and every further token is one decode step (LLARK_KV_CACHE=0: a full forward per token instead); extra keyword arguments the reference passes
         along (`labels`, `example_id`, `id`) are ignored as transformers ignores / rejects them."""
         from llark_b200.generate import generate_with_model
 
         state = {"cache": None}
 
         def step_logits(ids):
-            if os.environ.get("LLARK_KV_CACHE") == "1":  # staged: prefill once, then one token per step
+            if os.environ.get("LLARK_KV_CACHE", "1") != "0":  # prefill once, then one token per step
                 out = self.forward(input_ids=ids, audio_encodings=audio_encodings, past_key_values=state["cache"],
                                    use_cache=True, return_dict=True)
                 state["cache"] = out.past_key_values

@@ -76,7 +76,7 @@ def test_generate_cacheless_and_staged_kv_cache_agree(cpu_engine, monkeypatch):
 
     cfg, params, ids, enc = gen_inputs()
     model = _build(cfg, params)
-    monkeypatch.delenv("LLARK_KV_CACHE", raising=False)
+    monkeypatch.setenv("LLARK_KV_CACHE", "0")
     ref = model.generate(input_ids=ids, audio_encodings=enc, max_new_tokens=6)
     assert ref.shape == (1, ids.shape[1] + 6)
     with torch.no_grad():

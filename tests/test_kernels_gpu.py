@@ -63,8 +63,6 @@ def test_gemm_bf16(M, N, K, a_mn, b_mn, gemm_mode):
     assert _rel(out, ref) < 5e-3, (err, scale)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
-                    reason="shapes not yet run on a B200 (set LLARK_STAGED=1)")
 @pytest.mark.parametrize("M,N,K", [(1, 12288, 4096), (2, 2048, 512), (17, 4096, 11008), (32, 50372, 2048)])
 def test_gemm_very_few_rows(M, N, K, gemm_mode):
     """Fewer A rows than one TMA box (the box reads past the tensor and is zero-filled): the decode step of the KV-cache
@@ -80,8 +78,6 @@ def test_gemm_very_few_rows(M, N, K, gemm_mode):
     assert buf[:, N:].abs().sum().item() == 0
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
-                    reason="staged kernel that has not run on a B200 yet (set LLARK_STAGED=1)")
 @pytest.mark.parametrize("M,N,K", [(1, 12288, 4096), (1, 4096, 11008), (3, 22016, 4096), (8, 32004, 4096), (2, 72, 136)])
 def test_gemv_decode_linear(M, N, K):
     """llark_gemv (weight-streaming linear of the decode step) against fp32 math and against the GEMM core it replaces."""
@@ -347,8 +343,6 @@ def test_attention_fwd_bwd(B, S, NH, pad):
         assert _rel(got[:, :, i], g[:, :, i]) < 1.5e-2, name
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
-                    reason="sizes not yet run on a B200 (set LLARK_STAGED=1)")
 @pytest.mark.parametrize("B,S,NH,pad", [(1, 2048, 2, True),     # the reference's --model_max_length (train_llark.sh)
                                         (1, 4096, 1, False),    # upper edge of the tcgen05 kernels' envelope
                                         (1, 4160, 1, True)])    # beyond it: llark_attn_* must fall back to mma.sync
@@ -474,8 +468,6 @@ def test_cast_and_colsum():
     assert _rel(out, xb.float().sum(0)) < 4e-3
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LLARK_STAGED") != "1",
-                    reason="staged kernel that has not run on a B200 yet (set LLARK_STAGED=1)")
 @pytest.mark.parametrize("B,s_max,lens,NH", [(1, 64, [17], 2), (3, 300, [1, 300, 129], 4)])
 def test_attention_decode_step(B, s_max, lens, NH):
     ops = _ops()

@@ -245,11 +245,8 @@ def test_generate_greedy_decoding_without_cache():
         model.generate(input_ids=ids_c, audio_encodings=enc_c, do_sample=True)
 
 
-STAGED = pytest.mark.skipif(os.environ.get("LLARK_STAGED") != "1",
-                            reason="staged code path that has not run on a B200 yet (set LLARK_STAGED=1)")
 
 
-@STAGED
 def test_generate_with_kv_cache_matches_cacheless():
     """Prefill + single-token decode steps against the KV cache (LLARK_KV_CACHE=1) must pick the same tokens as the
     cache-less loop and reproduce its last-position logits (bf16 noise only)."""
@@ -258,7 +255,7 @@ def test_generate_with_kv_cache_matches_cacheless():
     cfg, params, ids, enc = gen_inputs()
     model = build_model(cfg, params)
     ids_c, enc_c = ids.cuda(), enc.cuda()
-    os.environ.pop("LLARK_KV_CACHE", None)
+    os.environ["LLARK_KV_CACHE"] = "0"
     ref = model.generate(input_ids=ids_c, audio_encodings=enc_c, max_new_tokens=8)
     with torch.no_grad():
         full = model(input_ids=ref[:, :-1], audio_encodings=enc_c).logits.float()
@@ -276,7 +273,6 @@ def test_generate_with_kv_cache_matches_cacheless():
     assert torch.equal(got, ref)
 
 
-@STAGED
 def test_activation_recompute_is_bit_identical_on_gpu(gold):
     """LLARK_RECOMPUTE=1 (what --gradient_checkpointing True selects under memory pressure): the backward regenerates each
     layer's activations from its input with the same kernels, so loss and every gradient match the plain step bit for
@@ -296,7 +292,6 @@ def test_activation_recompute_is_bit_identical_on_gpu(gold):
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
 
 
-@STAGED
 def test_wrapped_trainer_follows_the_reference_trajectory_on_gpu(tmp_path):
     """GPU twin of tests/test_trainstep_cpu.py: WrappedTrainer + the fused AdamW kernel on the CUDA engine against the
     reference's 4-step trajectory (tests/golden/trainstep_ref.pt). Written after the round's GPU budget was spent."""
@@ -310,7 +305,6 @@ def test_wrapped_trainer_follows_the_reference_trajectory_on_gpu(tmp_path):
     check_against_reference(trainer, model, gold_t, loss_tol=1e-2, delta_tol=0.05, cos_min=0.98)
 
 
-@STAGED
 def test_frozen_backbone_projector_only_training_on_gpu(gold):
     """GPU twin of tests/test_engine_host_cpu.py::test_frozen_backbone_projector_only_training (--freeze_backbone True):
     null weight-gradient pointers for every decoder tensor, dgrad through all layers, a bucket with two trainable tensors."""

@@ -1,8 +1,7 @@
-"""STAGED GPU tests of the MPT variant's kernels: bias-free LayerNorm fwd/bwd, exact GELU fwd/bwd, the
+"""GPU tests of the MPT variant's kernels: bias-free LayerNorm fwd/bwd, exact GELU fwd/bwd, the
 ALiBi instantiation of the tcgen05 attention, and the whole MPTEngine step against oracle/mpt_oracle.py (which
-tests/test_mpt_oracle_cpu.py pins to the reference's WrappedMPTForCausalLM).  These kernels were written after this
-round's GPU budget was spent and have NOT run on a B200 yet, so the tests only run with LLARK_STAGED=1 -- the first thing
-to do next round is `LLARK_STAGED=1 python -m pytest tests/test_mpt_gpu.py -m gpu`."""
+tests/test_mpt_oracle_cpu.py pins to the reference's WrappedMPTForCausalLM). First run on a B200 in round 2
+(profiles/r2a_staged_pytest.txt: all green)."""
 import math
 import os
 import sys
@@ -12,9 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(__file__))
 BF16 = torch.bfloat16
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LLARK_STAGED") != "1",
-                                 reason="staged kernels that have not run on a B200 yet (set LLARK_STAGED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _rel(a, b):
