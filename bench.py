@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="per-GPU micro-batch (samples)")
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers INVALIDATES the number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the configs[1] (Jukebox only) and configs[3] (end-to-end) measurements added to the line")
     ap.add_argument("--no-torch-baseline", action="store_true",
                     help="skip the stock-PyTorch run of the reference's model class on the same GPU (N=1 only)")
     ap.add_argument("--workload", default="llama", choices=["llama", "e2e"],
@@ -394,6 +396,85 @@ def gpu_torch_baseline(B, steps, warmup):
     return {"unavailable": f"out of memory at every batch size: {last_err}"}
 
 
+# ------------------------------------------------------------------------------------------------ Jukebox front end
+def jukebox_measure(precision="bf16", batch=8, steps=3, warmup=1, depth=36, objs=None):
+    """BASELINE configs[1]: Jukebox front end only -- 25 s @ 44.1 kHz synthetic waveforms -> [240, 4800] embeddings,
+    batch 8, 1 x B200, random weights of the upstream shapes (36-layer 5b prior). Per-stage CUDA-event timings and the
+    roofline numbers of SURVEY section 8(d): conv encoder GB/s against the 1.42 GB/clip fused-res-block traffic figure and
+    FP32 TFLOP/s against 41.2 GFLOP/clip; prior TFLOP/s against 40.77 TFLOP/clip (per-shape GEMM rates from events
+    around every launch); pool GB/s against 161.9 MB/clip."""
+    from llark_b200 import ops
+    from llark_b200.jukebox import main as jm
+    from llark_b200.jukebox.model import JukeboxConfig
+
+    if objs is None:
+        cfg = JukeboxConfig(prior_depth=depth)
+        _, vqvae, top_prior = jm.load_model("5b", cfg=cfg, precision=precision)
+    else:
+        vqvae, top_prior = objs
+        cfg = top_prior.cfg
+    g = torch.Generator().manual_seed(0)
+    wav = torch.rand(batch, 1102500, generator=g) * 2 - 1  # 25 s @ 44.1 kHz
+    peak = wav.abs().amax(dim=1, keepdim=True)
+    x = (wav / peak)[:, : cfg.sample_length].cuda().contiguous()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    stages = {"conv_encoder": 0.0, "vq": 0.0, "prior": 0.0, "pool": 0.0}
+    total = 0.0
+    prof = None
+    for it in range(warmup + steps):
+        e = [ev() for _ in range(5)]
+        if it == warmup + steps - 1:
+            ops.GEMM_PROFILE = []
+        e[0].record()
+        lat = vqvae.encode_top_latents(x[:, None, :].contiguous())
+        e[1].record()
+        z = ops.jb_vq_encode(lat, vqvae.w["codebook"])
+        e[2].record()
+        top_prior.prior.only_encode = True
+        acts = top_prior.prior.forward(z, None, None, None, False)
+        e[3].record()
+        pooled = jm.pool_batch(acts, cfg.n_ctx, 34)
+        e[4].record()
+        torch.cuda.synchronize()
+        if ops.GEMM_PROFILE is not None:
+            prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        if it >= warmup:
+            for k, (s0, s1) in zip(stages, zip(e[:-1], e[1:])):
+                stages[k] += s0.elapsed_time(s1)
+            total += e[0].elapsed_time(e[4])
+        del lat, z, acts
+    n = steps * batch
+    per_clip = {k: v / n for k, v in stages.items()}
+    scale = cfg.prior_depth / 36.0
+    by_shape = {}
+    for a, b, f, shp in prof or []:
+        t = by_shape.setdefault(f"M{shp[0]} N{shp[1]} K{shp[2]}", [0.0, 0.0, 0])
+        t[0] += f
+        t[1] += a.elapsed_time(b)
+        t[2] += 1
+    gemm_ms = sum(v[1] for v in by_shape.values())
+    by_shape = {k: {"tflops": round(v[0] / (v[1] / 1000.0) / 1e12, 1), "ms_total": round(v[1], 2), "launches": v[2]}
+                for k, v in by_shape.items()}
+    pk, _ = peaks()
+    conv_s = per_clip["conv_encoder"] / 1000.0
+    return {"workload": "configs[1]: Jukebox front end only, 25 s @ 44.1 kHz synthetic clips -> [240,4800], batch %d, "
+                        "1 GPU, levels 0/1 of the VQ-VAE skipped (dead work in the reference)" % batch,
+            "precision": {"conv_encoder": "fp32 SIMT" if not getattr(vqvae, "tensor_core", False) else "3xTF32 tcgen05",
+                          "prior": precision}, "prior_depth": cfg.prior_depth,
+            "clips_per_s": n / (total / 1000.0), "ms_per_clip": total / n, "ms_per_clip_by_stage": per_clip,
+            "conv_encoder": {"fp32_tflops": 41.2e-3 / conv_s, "gbs_vs_1p42GB_per_clip": 1.42 / conv_s,
+                             "frac_of_hbm_peak": 1.42 / conv_s / pk["hbm_gbs"]},
+            "prior": {"tflops": 40.77 * scale / (per_clip["prior"] / 1000.0),
+                      "frac_of_sustained_bf16_peak": 40.77 * scale / (per_clip["prior"] / 1000.0) /
+                      pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                      "gemm_share_of_prior": gemm_ms / (stages["prior"] / steps) if prof else None,
+                      "gemm_by_shape": by_shape},
+            "pool": {"gbs": 0.1619 / (per_clip["pool"] / 1000.0)}, "pooled_shape": list(pooled.shape)}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def build_model(layers):
     from llark_b200.models.llamav2 import WrappedLlamav2Config, WrappedLlamav2ForCausalLM
@@ -420,6 +501,47 @@ def build_model(layers):
     model.get_model().orig_embeds_params = [None]  # text-embedding rows detached (only the marker rows get grads)
     model.validate = "lazy"
     return model
+
+
+def measure_extras(args, model, opt, B, world, rank, timed):
+    from llark_b200.jukebox import main as jm
+
+    out = {}
+    _, vqvae, top_prior = jm.load_model("5b", precision=args.jukebox_precision)
+    if world == 1:
+        out["configs1_jukebox"] = jukebox_measure(args.jukebox_precision, batch=8, steps=2, warmup=1,
+                                                   objs=(vqvae, top_prior))
+    g = torch.Generator().manual_seed(77 + rank)
+    host = []
+    for i in range(2):
+        b = synth_batch(B, seed=2000 + rank + world * i)
+        del b["audio_encodings"]
+        b["waveform"] = torch.rand(B, 1102500, generator=g) * 2 - 1  # 25 s @ 44.1 kHz, mono
+        host.append({k: v.pin_memory() for k, v in b.items()})
+    chunk = 8  # clips per front-end pass (bounds the prior's fp32 activations at 1.26 GB per tensor)
+
+    def step(i):
+        b = {k: v.cuda(non_blocking=True) for k, v in host[i % 2].items()}
+        with torch.no_grad():
+            enc = torch.cat([jm.embed_batch(b["waveform"][j:j + chunk], vqvae, top_prior, pool_frames_per_second=10)
+                             for j in range(0, B, chunk)])
+        res = model(input_ids=b["input_ids"], labels=b["labels"], attention_mask=b["attention_mask"],
+                    audio_encodings=enc)
+        res.loss.backward()
+        opt.step()
+        return res.loss.item()
+
+    step(0)
+    steps = 2
+    ms, _ = timed(step, steps)
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    out["configs3_e2e"] = {
+        "workload": "configs[3]: end-to-end 25 s waveform (pinned host) -> Jukebox-5b front end (VQ-VAE level 2, 36-layer "
+                    f"prior {args.jukebox_precision}, pool) -> mm_projector -> Llama-2-7B training step, seq 512, bf16",
+        "value": B * world * steps / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": 1,
+        "per_gpu_batch": B, "global_batch": B * world, "n_gpus": world, "h2d_bytes_per_step": h2d,
+        "d2h_bytes_per_step": 4}
+    return out
 
 
 def main():
@@ -543,7 +665,19 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
 
+    # ---- the other BASELINE configs, measured in the same process and carried as extra fields of the one JSON line:
+    # configs[3] (waveform -> Jukebox front end -> projector -> Llama step, every N) and configs[1] (front end only, N=1)
+    extras = {}
+    if front is None and not args.no_extras and args.layers == 32:
+        try:
+            extras = measure_extras(args, model, opt, B, world, rank, timed)
+        except Exception as e:  # never take the headline down
+            extras = {"configs3_e2e": {"unavailable": f"failed: {e!r}"[:300]}}
     if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
         return
     pk, pk_kind = peaks()
     total_samples = B * world * args.steps
@@ -581,6 +715,8 @@ def main():
                      "flops_per_sample": fl["total"] / B, "gemm_by_shape": by_kind},
         "clocks": clocks,
     }
+    if extras:
+        line.update(extras)
     if torch_base is not None:
         line["gpu_torch_baseline"] = torch_base
         if torch_base.get("value"):

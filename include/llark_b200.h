@@ -231,6 +231,9 @@ int llark_quick_gelu(const float* x, float* y, long long n, cudaStream_t stream)
 int llark_add3(const float* a, const float* b, const float* c, float* out, long long n, cudaStream_t stream);
 /* AvgPool1d(frame, stride frame, floor) over time: acts [T, W] -> out [T/frame, W] (jukebox/main.py:113-130). */
 int llark_jb_pool(const float* acts, float* out, int T_valid, int W, int frame, cudaStream_t stream);
+/* the same pool over N clips in one launch: acts [N, clip_stride/W rows, W], out [N, T_valid/frame, W] */
+int llark_jb_pool_batched(const float* acts, float* out, int N, long long clip_stride, int T_valid, int W, int frame,
+                          cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ SYMBOLS = [
     "llark_comm_destroy", "llark_grad_bucket_allreduce", "llark_jb_conv_down", "llark_jb_resblock",
     "llark_jb_conv_k3", "llark_jb_vq_encode", "llark_layernorm_fwd", "llark_jb_embed_tokens", "llark_jb_sparse_attn",
     "llark_jb_sparse_attn_tc",
-    "llark_quick_gelu", "llark_add3", "llark_jb_pool", "llark_colsum",
+    "llark_quick_gelu", "llark_add3", "llark_jb_pool", "llark_jb_pool_batched", "llark_colsum",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def lib():
             "llark_quick_gelu": ([P, P, LL, P], I),
             "llark_add3": ([P, P, P, P, LL, P], I),
             "llark_jb_pool": ([P, P, I, I, I, P], I),
+            "llark_jb_pool_batched": ([P, P, I, LL, I, I, I, P], I),
             "llark_colsum": ([P, P, LL, I, I, P], I),
         }
         for name, (argtypes, restype) in sig.items():

@@ -605,13 +605,37 @@ __global__ void add3_kernel(const float* __restrict__ a, const float* __restrict
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = c ? (a[i] + b[i]) + c[i] : a[i] + b[i];
 }
-// out[f, c] = mean_{j<frame} acts[f*frame + j, c]
-__global__ void jb_pool_kernel(const float* __restrict__ acts, float* __restrict__ out, int W, int frame) {
+// out[n, f, c] = mean_{j<frame} acts[n, f*frame + j, c]; grid (frames, N, ceil(W/4/blockDim)), 4 columns per thread,
+// the `frame` row loads of a thread are independent (two accumulators) so a warp keeps ~frame x 512 B in flight.
+__global__ void jb_pool_kernel(const float* __restrict__ acts, float* __restrict__ out, long long clip_stride, int frames,
+                               int W, int frame) {
     const int f = blockIdx.x;
-    for (int c = threadIdx.x; c < W; c += blockDim.x) {
-        float s = 0.f;
-        for (int j = 0; j < frame; ++j) s += acts[((long long)f * frame + j) * W + c];
-        out[(long long)f * W + c] = s / (float)frame;
+    const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
+    if (c >= W) return;
+    const float* src = acts + (long long)blockIdx.y * clip_stride + (long long)f * frame * W + c;
+    float* dst = out + ((long long)blockIdx.y * frames + f) * W + c;
+    if (c + 4 <= W && (W & 3) == 0) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        int j = 0;
+        for (; j + 1 < frame; j += 2) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + (long long)j * W));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + (long long)(j + 1) * W));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+        }
+        if (j < frame) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + (long long)j * W));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+        const float inv = 1.f / (float)frame;
+        *reinterpret_cast<float4*>(dst) =
+            make_float4((s0.x + s1.x) * inv, (s0.y + s1.y) * inv, (s0.z + s1.z) * inv, (s0.w + s1.w) * inv);
+    } else {
+        for (int k = 0; k < 4 && c + k < W; ++k) {
+            float sum = 0.f;
+            for (int j = 0; j < frame; ++j) sum += src[(long long)j * W + k];
+            dst[k] = sum / (float)frame;
+        }
     }
 }
 // colsum over rows of a bf16 [rows, H] matrix -> bf16 [H] (bias gradient), fp32 accumulate.
@@ -773,12 +797,17 @@ extern "C" int llark_add3(const float* a, const float* b, const float* c, float*
     add3_kernel<<<ew_grid(n, 1), 256, 0, st>>>(a, b, c, out, n);
     return jb_check();
 }
-extern "C" int llark_jb_pool(const float* acts, float* out, int T_valid, int W, int frame, cudaStream_t st) {
-    if (frame <= 0 || W <= 0) return LLARK_EINVAL;
+extern "C" int llark_jb_pool_batched(const float* acts, float* out, int N, long long clip_stride, int T_valid, int W,
+                                     int frame, cudaStream_t st) {
+    if (frame <= 0 || W <= 0 || N <= 0) return LLARK_EINVAL;
     const int frames = T_valid / frame;
     if (frames <= 0) return LLARK_OK;
-    jb_pool_kernel<<<frames, 256, 0, st>>>(acts, out, W, frame);
+    dim3 grid(frames, N, (W + 1023) / 1024);
+    jb_pool_kernel<<<grid, 256, 0, st>>>(acts, out, clip_stride, frames, W, frame);
     return jb_check();
+}
+extern "C" int llark_jb_pool(const float* acts, float* out, int T_valid, int W, int frame, cudaStream_t st) {
+    return llark_jb_pool_batched(acts, out, 1, 0, T_valid, W, frame, st);
 }
 extern "C" int llark_colsum(const void* x, void* out, long long rows, int H, int accumulate, cudaStream_t st) {
     if (rows <= 0 || H <= 0) return LLARK_EINVAL;

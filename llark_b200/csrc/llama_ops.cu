@@ -171,7 +171,9 @@ __global__ void embed_splice_bwd_kernel(const long long* __restrict__ ids, const
     }
     if (!dtable) return;
     const bool marker = pos >= 0 && (s == pos || s == pos + F + 1);
-    if (detach_text && !marker) return;
+    // a sample without <audio_start> keeps its undetached embeddings in the reference (the loop body that detaches,
+    // llamav2.py:162-208, never runs for it), so every one of its text rows receives gradient
+    if (detach_text && !marker && pos >= 0) return;
     long long t = ids[(long long)b * S + s];
     if (t < 0 || t >= vocab) return;
     __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dtable + t * H);

@@ -204,10 +204,25 @@ class TarShardDataset(torch.utils.data.IterableDataset):
     ranks (wds.split_by_node) and dataloader workers; corrupt members are skipped with a warning
     (wds.warn_and_continue)."""
 
-    def __init__(self, urls, multimodal_cfg, tokenizer, is_train, rank=0, world=1, seed=0):
+    def __init__(self, urls, multimodal_cfg, tokenizer, is_train, rank=0, world=1, seed=0, rsample_frac=None,
+                 task_sample_probs=None, shuffle_buffer=100):
         self.urls = list(urls)
         self.cfg, self.tokenizer, self.is_train = multimodal_cfg, tokenizer, is_train
         self.rank, self.world, self.seed = rank, world, seed
+        self.rsample_frac, self.shuffle_buffer = rsample_frac, shuffle_buffer
+        # shard weights of the training stream (repeat_shards, m2t/data_modules.py:441-463): the first
+        # task_sample_probs key found in a shard's name; a shard no key matches is a ValueError
+        self.weights = None
+        if is_train and task_sample_probs is not None:
+            logging.warning(f"applying task probs {task_sample_probs}")
+            self.weights = []
+            for shard in self.urls:
+                hit = next((p for key, p in task_sample_probs.items() if key in shard), None)
+                if hit is None:
+                    raise ValueError(f"probability for shard {shard} not defined in probs {task_sample_probs}")
+                self.weights.append(hit)
+        if not self.urls:
+            raise ValueError("TarShardDataset needs at least one shard")
 
     def _elements(self, path):
         cur_key, cur = None, {}
@@ -232,22 +247,49 @@ class TarShardDataset(torch.utils.data.IterableDataset):
             if cur:
                 yield cur
 
+    def _shard_stream(self, rng, wid, nw):
+        """Training (wds `resampled=True` over the repeat_shards list, m2t/data_modules.py:484-498): EVERY rank and
+        worker draws shards with replacement from the full list (weighted by task_sample_probs), each from its own
+        seeded generator, so no rank starves when there are fewer shards than ranks x workers. Evaluation: one pass over
+        the shards of this rank / worker (wds.split_by_node + split_by_worker)."""
+        if self.is_train:
+            while True:
+                yield rng.choices(self.urls, weights=self.weights, k=1)[0]
+        else:
+            yield from self.urls[self.rank::self.world][wid::nw]
+
     def __iter__(self):
         info = torch.utils.data.get_worker_info()
         wid, nw = (info.id, info.num_workers) if info else (0, 1)
-        shards = self.urls[self.rank::self.world][wid::nw]
         rng = random.Random(self.seed + 1000 * self.rank + wid)
         mm = partial(preprocess_multimodal_mappable, multimodal_cfg=self.cfg)
         lm = partial(preprocess_for_lm_mappable, tokenizer=self.tokenizer)
-        while True:
-            order = list(shards)
-            if self.is_train:
-                rng.shuffle(order)
-            for path in order:
-                for e in webdataset_element_to_conversation(self._elements(path)):
-                    yield lm(mm(e))
-            if not self.is_train:
+
+        def conversations():
+            for path in self._shard_stream(rng, wid, nw):
+                yield from webdataset_element_to_conversation(self._elements(path))
+
+        def shuffled(it):
+            # wds `.shuffle(100)` (:510-511): a 100-element buffer between the per-clip Q/A expansion and tokenisation,
+            # so the Q/A pairs of one clip do not arrive back to back; applied when training or sub-sampling
+            if not (self.is_train or self.rsample_frac is not None) or self.shuffle_buffer <= 1:
+                yield from it
                 return
+            buf = []
+            for e in it:
+                if len(buf) < self.shuffle_buffer:
+                    buf.append(e)
+                    continue
+                k = rng.randrange(self.shuffle_buffer)
+                yield buf[k]
+                buf[k] = e
+            rng.shuffle(buf)
+            yield from buf
+
+        for e in shuffled(conversations()):
+            if self.rsample_frac and rng.random() >= self.rsample_frac:  # wds `.rsample(p)` (:512-513)
+                continue
+            yield lm(mm(e))
 
 
 def expand_url_to_file_list(url: str) -> List[str]:
@@ -508,9 +550,12 @@ def make_data_module(tokenizer, data_args, data_collator_cls=DataCollatorForSupe
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     train_dataset = eval_dataset = None
     if data_args.train_data_path:
+        probs = (getattr(data_args, "task_sample_probs", None)
+                 if getattr(data_args, "apply_task_sample_probs", False) else None)
         train_dataset = TarShardDataset(expand_url_to_file_list(data_args.train_data_path), multimodal_cfg, tokenizer,
-                                        True, rank, world)
+                                        True, rank, world, task_sample_probs=probs)
     if data_args.eval_data_path:
         eval_dataset = TarShardDataset(expand_url_to_file_list(data_args.eval_data_path), multimodal_cfg, tokenizer,
-                                       False, rank, world)
+                                       False, rank, world,
+                                       rsample_frac=getattr(data_args, "eval_data_subsample", None))
     return dict(train_dataset=train_dataset, eval_dataset=eval_dataset, data_collator=data_collator_cls(tokenizer=tokenizer))

@@ -160,7 +160,13 @@ def embed_batch(waveforms, vqvae, top_prior, pool_frames_per_second=10):
     acts = top_prior.prior.forward(z[:, : cfg.n_ctx], x_cond=None, y_cond=None, encoder_kv=None, fp16=False)
     valid = min(latent_len, cfg.n_ctx)
     frame_len = floor((cfg.n_ctx / (expected / JUKEBOX_SAMPLE_RATE)) / pool_frames_per_second)
-    return torch.stack([ops.jb_pool(acts[i, :valid].contiguous(), valid, frame_len) for i in range(acts.shape[0])])
+    return pool_batch(acts, valid, frame_len)
+
+
+def pool_batch(acts, valid, frame_len):
+    """windowed_average (jukebox/main.py:113-130) of the first `valid` positions of every clip of acts [N, T, W] in one
+    launch (no per-clip copies): -> fp32 [N, valid // frame_len, W]."""
+    return ops.jb_pool_batched(acts.float().contiguous(), valid, frame_len)
 
 
 def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0):

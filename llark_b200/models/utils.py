@@ -119,6 +119,12 @@ def load_pretrained_model(model_name: str, ckpt_num: int, torch_dtype=torch.floa
     if sharded:
         print("[DEBUG] loading mm projector parameters")
         load_sharded_mm_projector_weights(model, ckpt_dir)
+    elif not is_mpt:
+        # Deviation from upstream, which fills the projector only from shards (HF save_pretrained always shards a 7B
+        # model): llark_b200's WrappedTrainer._save writes ONE pytorch_model.bin, from_pretrained drops its
+        # `model.mm_projector.*` keys as unexpected (the module does not exist yet), so read them here -- otherwise
+        # inference on such a checkpoint would run with the random projector initialize_adapter_modules just created.
+        _load_shard_into(model, os.path.join(ckpt_dir, WEIGHTS_NAME))
     model.to(device)
     model.get_model().mm_projector.to(device)
     model.config.mm_use_audio_start_end = mm_use_audio_start_end

@@ -362,6 +362,17 @@ def add3(a, b, c=None, out=None):
     return out
 
 
+def jb_pool_batched(acts, T_valid, frame):
+    """acts fp32 [N, T, W] (contiguous) -> [N, T_valid // frame, W]: windowed mean over time of every clip, one launch."""
+    _req(acts, torch.float32)
+    N, T, W = acts.shape
+    if not acts.is_contiguous() or T_valid > T:
+        raise ValueError("jb_pool_batched needs a contiguous [N, T, W] tensor with T >= T_valid")
+    out = torch.empty((N, T_valid // frame, W), device=acts.device, dtype=torch.float32)
+    check(lib().llark_jb_pool_batched(_p(acts), _p(out), N, T * W, T_valid, W, frame, _stream()), "jb_pool_batched")
+    return out
+
+
 def jb_pool(acts, T_valid, frame):
     W = acts.shape[1]
     out = torch.empty((T_valid // frame, W), device=acts.device, dtype=torch.float32)

@@ -146,6 +146,10 @@ class WrappedTrainer:
         if resume_from_checkpoint:
             self._load_from_checkpoint(resume_from_checkpoint)
         dev = next(self.model.parameters()).device
+        if resume_from_checkpoint and self.state["global_step"] and hasattr(self.train_dataset, "seed"):
+            # do not replay the samples the interrupted run already consumed: the resumed stream draws its shards and
+            # shuffle buffer from a generator offset by the restored step count
+            self.train_dataset.seed = int(self.train_dataset.seed) + 7919 * int(self.state["global_step"])
         it = self._batches()
         self.model.train()
         t0 = time.time()
@@ -161,10 +165,12 @@ class WrappedTrainer:
                 out = self.model(**batch)
                 (out.loss / accum).backward()
                 losses.append(out.loss.detach())
+            # the reference raises its splice ValueErrors (llamav2.py:146-175) inside forward, i.e. BEFORE the update is
+            # applied: read the device flag word (one 4-byte sync per optimizer step) before stepping
+            self.model.check_audio_token_errors()
             self.optimizer.step()
             self.state["global_step"] += 1
             if self.state["global_step"] % max(1, self._arg("logging_steps", 1)) == 0:
-                self.model.check_audio_token_errors()
                 entry = {"step": self.state["global_step"], "loss": torch.stack(losses).mean().item(),
                          "learning_rate": self.optimizer.param_groups[0]["lr"],
                          "grad_norm": self.optimizer.grad_norm().item(), "elapsed_s": time.time() - t0}
@@ -177,8 +183,10 @@ class WrappedTrainer:
             save_steps = self._arg("save_steps", 0)
             if save_steps and self.state["global_step"] % save_steps == 0 and self._is_main():
                 ckpt = os.path.join(self._arg("output_dir", "."), f"checkpoint-{self.state['global_step']}")
-                self._save(ckpt)
+                self._save(ckpt)  # (the mm_projector side file is keyed by this folder name)
                 self._save_optimizer(ckpt)
+                with open(os.path.join(ckpt, "COMPLETE"), "w") as f:  # written last: marks a fully written folder
+                    f.write(str(self.state["global_step"]))
                 self._rotate_checkpoints()
         return self.state
 
@@ -197,7 +205,10 @@ class WrappedTrainer:
             m = re.fullmatch(r"checkpoint-(\d+)", name)
             if m and os.path.isdir(os.path.join(out, name)):
                 found.append((int(m.group(1)), name))
-        for _, name in sorted(found)[:-limit]:
+        found.sort()
+        if found and not os.path.exists(os.path.join(out, found[-1][1], "COMPLETE")):
+            return  # never delete older checkpoints on the strength of a partially written newest one
+        for _, name in found[:-limit]:
             logging.warning(f"deleting older checkpoint {name} (save_total_limit={limit})")
             shutil.rmtree(os.path.join(out, name), ignore_errors=True)
 
@@ -267,7 +278,9 @@ class WrappedTrainer:
         path = resume_from_checkpoint
         if path is True:
             out = self._arg("output_dir", ".")
-            cks = sorted((d for d in os.listdir(out) if d.startswith("checkpoint-")), key=lambda s: int(s.split("-")[1]))
+            cks = sorted((d for d in os.listdir(out) if d.startswith("checkpoint-")
+                          and os.path.exists(os.path.join(out, d, "pytorch_model.bin"))),
+                         key=lambda s: int(s.split("-")[1]))
             if not cks:
                 return
             path = os.path.join(out, cks[-1])

@@ -273,7 +273,7 @@ def embed_splice_bwd(ids, dout, daudio, audio_off, frames, start_pos, dtable, vo
             if dtable is None:
                 continue
             marker = p >= 0 and (s_ == p or s_ == p + F_ + 1)
-            if detach_text and not marker:
+            if detach_text and not marker and p >= 0:  # an audio-less sample stays undetached (llamav2.py:162-208)
                 continue
             t = int(ids[b, s_])
             dtable[t] = (dtable[t].float() + dout[b, s_].float()).to(BF16)
@@ -381,6 +381,11 @@ def add3(a, b, c=None, out=None):
 def jb_pool(acts, T_valid, frame):
     n = T_valid // frame
     return acts[: n * frame].view(n, frame, -1).mean(1)
+
+
+def jb_pool_batched(acts, T_valid, frame):
+    n = T_valid // frame
+    return acts[:, : n * frame].reshape(acts.shape[0], n, frame, -1).mean(2)
 
 
 # ------------------------------------------------------------------------------------------------ MPT variant (staged ops)

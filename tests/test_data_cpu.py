@@ -103,3 +103,22 @@ def test_tar_shard_reader_and_make_data_module(tmp_path):
     k0 = {i["example_id"] for i in r0}
     k1 = {i["example_id"] for i in r1}
     assert k0 and k1 and not (k0 & k1)
+    # a training rank never starves -- with ONE shard and two ranks both ranks draw from it (wds
+    # resampled=True), the Q/A pairs of a clip are spread by the 100-element buffer, and shard weights follow
+    # task_sample_probs; eval_data_subsample thins the evaluation stream
+    import itertools
+
+    random.seed(0)
+    one = dm.TarShardDataset(paths[:1], dm.make_mm_config(args), tok, True, rank=1, world=2)
+    got = list(itertools.islice(iter(one), 20))
+    assert len(got) == 20
+    w = dm.TarShardDataset(paths, dm.make_mm_config(args), tok, True, rank=0, world=1,
+                           task_sample_probs={"train-000": 1.0, "train-001": 0.0})
+    ids = {i["example_id"] for i in itertools.islice(iter(w), 30)}
+    assert ids and all(str(i).endswith("s0") for i in ids), ids
+    with pytest.raises(ValueError):
+        dm.TarShardDataset(paths, dm.make_mm_config(args), tok, True, task_sample_probs={"nomatch": 1.0})
+    random.seed(0)
+    args.eval_data_subsample = 0.5
+    thin = list(dm.make_data_module(tok, args)["eval_dataset"])
+    assert 0 < len(thin) < len(items)

@@ -101,3 +101,37 @@ def test_infer_cli_over_embedding_folder(run_dir, tmp_path):
     assert list(df.columns) == ["example_id", "prompt_text", "model_completion_text"]
     assert sorted(os.path.basename(e) for e in df["example_id"]) == ["song0", "song1"]
     assert (df["prompt_text"] == "What genre is this song?").all()
+
+
+def test_trainer_save_then_load_pretrained_model_keeps_the_projector(run_dir, tmp_path):
+    """WrappedTrainer._save writes a single pytorch_model.bin; load_pretrained_model must bring the
+    trained mm_projector back (upstream only reads it from shards) instead of a freshly initialised nn.Linear."""
+    from types import SimpleNamespace
+
+    from transformers import AutoTokenizer
+
+    from llark_b200.models.llamav2 import WrappedLlamav2ForCausalLM
+    from llark_b200.models.utils import load_pretrained_model
+    from llark_b200.trainer import WrappedTrainer
+
+    name, _ = run_dir
+    src = os.path.join(name, "checkpoint-5")
+    tok = AutoTokenizer.from_pretrained(src)
+    model, _ = load_pretrained_model(name, 5, torch_dtype=torch.float32, device="cpu")
+    with torch.no_grad():   # "trained" projector and embedding rows
+        g = torch.Generator().manual_seed(3)
+        model.get_model().mm_projector.weight.copy_(torch.randn(model.get_model().mm_projector.weight.shape, generator=g))
+        model.get_model().mm_projector.bias.copy_(torch.randn(model.get_model().mm_projector.bias.shape, generator=g))
+        model.get_input_embeddings().weight[-2:].add_(1.0)
+    trainer = WrappedTrainer.__new__(WrappedTrainer)
+    trainer.model, trainer.tokenizer = model, tok
+    trainer.args = SimpleNamespace(tune_mm_mlp_adapter=False)
+    dst = os.path.join(name, "checkpoint-9")
+    trainer._save(dst)
+    assert os.path.exists(os.path.join(dst, "pytorch_model.bin"))
+    back, _ = load_pretrained_model(name, 9, torch_dtype=torch.float32, device="cpu")
+    assert isinstance(back, WrappedLlamav2ForCausalLM)
+    for attr in ("weight", "bias"):
+        assert torch.equal(getattr(back.get_model().mm_projector, attr).float(),
+                           getattr(model.get_model().mm_projector, attr).float()), attr
+    assert torch.equal(back.get_input_embeddings().weight.float(), model.get_input_embeddings().weight.float())

@@ -123,6 +123,13 @@ def test_pool_matches_reference_golden():
     assert tuple(pooled.shape) == ref["shape"]
     assert torch.allclose(pooled[:, :64], ref["pooled_head"], atol=1e-6)
     assert abs(pooled.double().sum().item() - ref["pooled_sum"]) < 1e-3
+    # the batched launch (embed_batch): every clip pooled as the per-clip call pools it, odd widths / tails included
+    for N, T, W, valid, frame in ((3, 700, 4800, 700, 34), (2, 64, 50, 61, 7), (1, 40, 4, 40, 1)):
+        a = torch.randn(N, T, W, generator=torch.Generator().manual_seed(T)).cuda()
+        got = jm.pool_batch(a, valid, frame)
+        n = valid // frame
+        want = a[:, : n * frame].reshape(N, n, frame, W).double().mean(2)
+        assert got.shape == (N, n, W) and torch.allclose(got.double(), want, atol=1e-6)
 
 
 def test_get_acts_from_file_end_to_end_tiny():
