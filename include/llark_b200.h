@@ -28,6 +28,9 @@ extern "C" {
 
 /* Last CUDA / driver / NCCL error code seen by the calling thread (for LLARK_ECUDA / EDRIVER / ENCCL). */
 int llark_last_cuda_error(void);
+/* One-time per-process set-up on the current device (TMA descriptor encoder, tile-counter ring of the GEMM scheduler).
+ * The only entry point that allocates or synchronises; every other llark_* call just enqueues on the caller's stream. */
+int llark_init(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * GEMM core (tcgen05 / TMEM / TMA).  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ R[M,N]), fp32 accumulate.
@@ -234,6 +237,23 @@ int llark_jb_pool(const float* acts, float* out, int T_valid, int W, int frame, 
 /* the same pool over N clips in one launch: acts [N, clip_stride/W rows, W], out [N, T_valid/frame, W] */
 int llark_jb_pool_batched(const float* acts, float* out, int N, long long clip_stride, int T_valid, int W, int frame,
                           cudaStream_t stream);
+
+/* ---- fp32 verification path of the Llama forward (csrc/verify_fp32.cu): what llark_b200/verify.py runs to check
+ * north_star's "fp32 logits within 1e-3 relative" against the reference's fp32 run of m2t/models/llamav2.py:259-337
+ * (transformers LlamaModel: LlamaRMSNorm, rotate_half RoPE, eager softmax attention, SiLU(gate)*up, shifted mean CE).
+ * All tensors fp32. The linears are llark_gemm(in_fp32=1) composed as 3xTF32 from llark_v32_split_tf32's halves. */
+int llark_v32_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t stream);
+int llark_v32_embed_splice_fwd(const long long* ids, const float* table, const float* audio, const long long* audio_off,
+                               const int* frames, const int* start_pos, float* out, int B, int S, int H, long long vocab,
+                               cudaStream_t stream);
+int llark_v32_rmsnorm_fwd(const float* x, const float* w, float* y, long long rows, int H, float eps, cudaStream_t stream);
+int llark_v32_rope(float* qkv, const float* cos_t, const float* sin_t, long long rows, int S, int n_rot_heads, int D,
+                   long long ld, cudaStream_t stream);
+int llark_v32_swiglu_fwd(const float* gu, float* act, long long rows, int I, cudaStream_t stream);
+int llark_v32_attn_fwd(const float* qkv, const unsigned char* key_mask, float* out, int B, int S, int n_heads, int D,
+                       float scale, cudaStream_t stream);
+int llark_v32_ce_fwd(const float* logits, long long ldv, int V, const long long* labels, int B, int S, float* row_loss,
+                     float* loss_out, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,14 @@ constexpr int kThreads = 256;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_KB;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_KB;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// Epilogue staging: every epilogue warp owns a [32 rows][32 + 4 pad fp32] patch of shared memory through which a 32-column
+// accumulator chunk is transposed from "one row per thread" (what tcgen05.ld delivers) to "a quarter-warp per row", so
+// that the residual loads and the C stores of a warp instruction cover whole 128 B (fp32) / 64 B (bf16) row segments
+// instead of 32 different rows (see epilogue_tile_staged).
+constexpr int EPI_LD = 36;                        // floats per staged row; 36 = 32 + 4 keeps float4 rows conflict-free
+constexpr int EPI_WARP_BYTES = 32 * EPI_LD * 4;   // 4608 B per epilogue warp
+constexpr int EPI_STAGE_BYTES = 4 * EPI_WARP_BYTES;
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 
 struct GemmParams {
     int M, N, K;
@@ -254,6 +261,230 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, long long row
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Staged (coalesced) epilogue. tcgen05.ld hands every thread 32 consecutive columns of ONE accumulator row, so direct
+// 16 B stores make each warp instruction touch 32 different rows (32 L2 sectors, half-filled) -- measured at ~35 us per
+// 256x256 fp32 tile with a residual, more than the MMA time of the tile for K <= 4800. Here the chunk goes through the
+// warp's shared-memory patch and comes back with a quarter-warp (fp32: 8 lanes x 16 B = 128 B) or an eighth-warp (bf16:
+// 4 lanes x 16 B = 64 B) per row: full sectors, 8x / 4x fewer memory transactions per instruction. The residual (or the
+// gate|up operand of the SwiGLU backward) of chunk c+1 is requested before chunk c is finished, so its latency overlaps
+// the TMEM read and the transpose. Every output element is still produced by exactly the arithmetic of
+// epilogue_store_chunk (same order of bias / activation / residual / rounding), and the thread that reads R[row, col]
+// is the one that writes C[row, col], so C may alias R (in-place accumulation).
+template <int EPI>
+__device__ __forceinline__ void epi_staged_f32(const GemmParams& p, long long row0, int ncol0, uint32_t taddr, float* stg,
+                                               int lane) {
+    const int rsub = lane >> 3, cq = (lane & 7) * 4;
+    float* const C = reinterpret_cast<float*>(p.C);
+    const float* const R = reinterpret_cast<const float*>(p.R);
+    const int nchunks = min(BLOCK_N / 32, (p.N - ncol0 + 31) / 32);  // warp-uniform
+    float4 rc[8], rn[8];
+    auto load_res = [&](int col0, float4 (&r)[8]) {
+        const int col = col0 + cq;
+        const int nc = p.N - col;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long row = row0 + i * 4 + rsub;
+            r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row >= p.M || nc <= 0) continue;
+            const float* rp = R + row * p.ldr + col;
+            if (nc >= 4) {
+                r[i] = *reinterpret_cast<const float4*>(rp);
+            } else {
+                r[i].x = rp[0];
+                if (nc > 1) r[i].y = rp[1];
+                if (nc > 2) r[i].z = rp[2];
+            }
+        }
+    };
+    if (R) load_res(ncol0, rc);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        const int col0 = ncol0 + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        float* srow = stg + lane * EPI_LD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + 4 * j) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        if (R && c + 1 < nchunks) load_res(col0 + 32, rn);
+        const int col = col0 + cq;
+        const int nc = p.N - col;
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias && nc > 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (e < nc)
+                    b[e] = p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[col + e]
+                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[col + e]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            const long long row = row0 + r;
+            const float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_LD + cq);
+            if (row >= p.M || nc <= 0) continue;
+            float f[4] = {a.x + b[0], a.y + b[1], a.z + b[2], a.w + b[3]};
+            if constexpr (EPI == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = f[e] / (1.f + __expf(-1.702f * f[e]));
+            }
+            if (R) {
+                f[0] += rc[i].x; f[1] += rc[i].y; f[2] += rc[i].z; f[3] += rc[i].w;
+            }
+            float* cp = C + row * p.ldc + col;
+            if (nc >= 4) {
+                *reinterpret_cast<float4*>(cp) = make_float4(f[0], f[1], f[2], f[3]);
+            } else {
+                for (int e = 0; e < nc; ++e) cp[e] = f[e];
+            }
+        }
+        __syncwarp();  // the patch is rewritten by the next chunk
+        if (R) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rc[i] = rn[i];
+        }
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_staged_bf16(const GemmParams& p, long long row0, int ncol0, uint32_t taddr, float* stg,
+                                                int lane) {
+    const int rsub = lane >> 2, cq = (lane & 3) * 8;
+    __nv_bfloat16* const C = reinterpret_cast<__nv_bfloat16*>(p.C);
+    // operand streamed alongside the accumulator: the residual R, or (EPI 3) gu = gate | up of the SwiGLU backward
+    const __nv_bfloat16* const X = EPI == 3 ? reinterpret_cast<const __nv_bfloat16*>(p.epi_a)
+                                            : reinterpret_cast<const __nv_bfloat16*>(p.R);
+    const long long ldx = EPI == 3 ? p.epi_ld : p.ldr;
+    const int nchunks = min(BLOCK_N / 32, (p.N - ncol0 + 31) / 32);  // warp-uniform
+    uint4 xc[4], xn[4], uc[4], un[4];  // uc / un: the `up` half (EPI 3 only)
+    auto load_x = [&](int col0, uint4 (&x)[4], uint4 (&u)[4]) {
+        const int col = col0 + cq;
+        const int nc = p.N - col;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long row = row0 + i * 8 + rsub;
+            x[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (EPI == 3) u[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (row >= p.M || nc <= 0) continue;
+            const __nv_bfloat16* xp = X + row * ldx + col;
+            if (nc >= 8) {
+                x[i] = *reinterpret_cast<const uint4*>(xp);
+                if (EPI == 3) u[i] = *reinterpret_cast<const uint4*>(xp + p.N);
+            } else {  // N tail (never taken by EPI 3: N % 8 == 0 is checked on the host)
+                __nv_bfloat16 t[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] = e < nc ? xp[e] : __float2bfloat16_rn(0.f);
+                x[i] = *reinterpret_cast<const uint4*>(t);
+            }
+        }
+    };
+    if (X) load_x(ncol0, xc, uc);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        const int col0 = ncol0 + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        float* srow = stg + lane * EPI_LD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + 4 * j) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        if (X && c + 1 < nchunks) load_x(col0 + 32, xn, un);
+        const int col = col0 + cq;
+        const int nc = p.N - col;
+        float b[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) b[e] = 0.f;
+        if (p.bias && nc > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < nc)
+                    b[e] = p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[col + e]
+                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[col + e]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + rsub;
+            const long long row = row0 + r;
+            const float4 a0 = *reinterpret_cast<const float4*>(stg + r * EPI_LD + cq);
+            const float4 a1 = *reinterpret_cast<const float4*>(stg + r * EPI_LD + cq + 4);
+            if (row >= p.M || nc <= 0) continue;
+            float f[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3],
+                          a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
+            __nv_bfloat16* cp = C + row * p.ldc + col;
+            if constexpr (EPI == 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = f[e] / (1.f + __expf(-1.702f * f[e]));
+            } else if constexpr (EPI == 3) {
+                // same arithmetic as the EPI 3 branch of epilogue_store_chunk / swiglu_bwd_kernel (llama_ops.cu)
+                const float2 g0 = unpack_bf16x2(xc[i].x), g1 = unpack_bf16x2(xc[i].y), g2 = unpack_bf16x2(xc[i].z),
+                             g3 = unpack_bf16x2(xc[i].w);
+                const float2 u0 = unpack_bf16x2(uc[i].x), u1 = unpack_bf16x2(uc[i].y), u2 = unpack_bf16x2(uc[i].z),
+                             u3 = unpack_bf16x2(uc[i].w);
+                const float g[8] = {g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, g3.x, g3.y};
+                const float u[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+                float dg[8], du[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float d = bf16_round(f[e]);
+                    const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
+                    const float silu = g[e] * sg;
+                    du[e] = d * bf16_round(silu);
+                    dg[e] = d * u[e] * (sg * (1.f + g[e] * (1.f - sg)));
+                }
+                st8_bf16(cp, dg);
+                st8_bf16(cp + p.N, du);
+                continue;
+            }
+            if (EPI != 3 && X) {
+                const float2 r0 = unpack_bf16x2(xc[i].x), r1 = unpack_bf16x2(xc[i].y), r2 = unpack_bf16x2(xc[i].z),
+                             r3 = unpack_bf16x2(xc[i].w);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+            }
+            if (nc >= 8) {
+                st8_bf16(cp, f);
+            } else {
+                for (int e = 0; e < nc; ++e) cp[e] = __float2bfloat16_rn(f[e]);
+            }
+        }
+        __syncwarp();  // the patch is rewritten by the next chunk
+        if (X) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xc[i] = xn[i];
+                if (EPI == 3) uc[i] = un[i];
+            }
+        }
+    }
+}
+
+// Epilogue of one 128 x 256 accumulator tile for the warp owning TMEM lanes [32 ew, 32 ew + 32): rows row0 .. row0 + 31.
+// The RoPE columns of a fused-QKV projection keep the row-per-thread path (rotation partners are 64 columns apart);
+// everything else is staged. debug bit 64 = the old direct path everywhere (A/B measurements).
+template <int EPI>
+__device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, long long row0, int lane, int ncol0, uint32_t taddr,
+                                                  float* stg) {
+    if ((EPI == 2 && ncol0 < p.epi_i1) || (p.debug & 64)) {
+        const long long row = row0 + lane;
+        epilogue_tile<EPI>(p, row, row < p.M, ncol0, taddr);
+        return;
+    }
+    if (p.c_fp32) {
+        if constexpr (EPI == 0 || EPI == 1) epi_staged_f32<EPI>(p, row0, ncol0, taddr, stg, lane);
+    } else {
+        epi_staged_bf16<EPI>(p, row0, ncol0, taddr, stg, lane);
+    }
+}
+
 template <int A_MN, int B_MN, int TF32, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -265,6 +496,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + kAccStages;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    float* epi_stage = reinterpret_cast<float*>(smem + kStages * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -391,9 +623,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const long long row = (long long)tc.m_blk * BLOCK_M + ew * 32 + lane;
-            const bool row_ok = row < p.M;
-            epilogue_tile<EPI>(p, row, row_ok, tc.n_blk * BLOCK_N, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N);
+            const long long row0 = (long long)tc.m_blk * BLOCK_M + ew * 32;
+            epilogue_dispatch<EPI>(p, row0, lane, tc.n_blk * BLOCK_N, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N,
+                                   epi_stage + ew * (EPI_WARP_BYTES / 4));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -418,7 +650,7 @@ constexpr int kStages2 = 6;
 constexpr int kSched = 4;  // depth of the tile-index ring of the dynamic scheduler
 constexpr int B2_STAGE_BYTES = 128 * BLOCK_KB;  // this CTA's half of B: 16 KB
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;  // 32 KB per CTA per stage
-constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 512;
+constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 512 + EPI_STAGE_BYTES;
 
 template <int A_MN, int B_MN, int TF32, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -436,6 +668,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     uint64_t* sched_empty = sched_full + kSched;      // [kSched] leader's: all 13 consumers of the pair have read it
     uint32_t* sched_tile = reinterpret_cast<uint32_t*>(sched_empty + kSched);  // [kSched]
     uint32_t* tmem_base_slot = sched_tile + kSched;
+    float* epi_stage = reinterpret_cast<float*>(smem + kStages2 * STAGE2_BYTES + 512);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -658,9 +891,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const long long row = (long long)tc.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane;
-            const bool row_ok = row < p.M;
-            epilogue_tile<EPI>(p, row, row_ok, tc.n_blk * BLOCK_N, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N);
+            const long long row0 = (long long)tc.m_blk * 256 + (long long)rank * 128 + ew * 32;
+            epilogue_dispatch<EPI>(p, row0, lane, tc.n_blk * BLOCK_N, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N,
+                                   epi_stage + ew * (EPI_WARP_BYTES / 4));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_empty0 + (uint32_t)as * 8u);
@@ -902,6 +1135,16 @@ static int g_gemm_mode = -1;  // -1: read LLARK_GEMM_2CTA from the environment o
 using namespace llark;
 
 extern "C" int llark_last_cuda_error(void) { return g_last_cuda_error; }
+
+// One-time, per-process set-up for the current device: resolves the driver entry point used to encode TMA descriptors
+// and allocates + zeroes the 16 KB ring of tile counters of the dynamic GEMM scheduler. This is the ONLY place that
+// allocates or synchronises; after it every llark_* call only enqueues work on the caller's stream. (llark_gemm still
+// initialises lazily if the caller skipped this, so old callers keep working, at the price of a first-call sync.)
+extern "C" int llark_init(void) {
+    int rc = ensure_driver();
+    if (rc != LLARK_OK) return rc;
+    return next_tile_counter() ? LLARK_OK : LLARK_ECUDA;
+}
 
 extern "C" void llark_gemm_set_mode(int two_cta) { g_gemm_mode = two_cta ? 1 : 0; }
 extern "C" int llark_gemm_get_mode(void) {

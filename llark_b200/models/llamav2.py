@@ -119,6 +119,16 @@ class WrappedLlamav2ForCausalLM(LlamaForCausalLM):
         """Same signature and return value as m2t/models/llamav2.py:259-337. Training / scoring / cache-less
         generation. `past_key_values` / `use_cache=True` run the KV-cache path (prefill + one-token decode steps,
         SURVEY §8(f) row 2; verified on a B200 against the cache-less loop, tests/test_model_gpu.py)."""
+        if os.environ.get("LLARK_VERIFY") == "fp32":
+            # fp32 verification mode (north_star: fp32 logits within 1e-3 relative of the reference's fp32 run):
+            # forward only, fp32 tensors end to end on the 3xTF32 tcgen05 path -- llark_b200/verify.py
+            from llark_b200.verify import forward_fp32
+
+            if torch.is_grad_enabled() and labels is not None and any(p.requires_grad for p in self.parameters()):
+                raise RuntimeError("LLARK_VERIFY=fp32 is a forward-only checking mode: call it under torch.no_grad()")
+            loss, logits = forward_fp32(self, input_ids, attention_mask, labels, audio_encodings)
+            return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=None,
+                                          attentions=None)
         if past_key_values is not None or use_cache:
             if os.environ.get("LLARK_KV_CACHE", "1") == "0":
                 raise NotImplementedError("KV-cache decoding is switched off (LLARK_KV_CACHE=0): generate() then runs "

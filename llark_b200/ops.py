@@ -18,6 +18,18 @@ BF16 = torch.bfloat16
 GEMM_PROFILE = None
 
 
+_INITED = False
+
+
+def init():
+    """llark_init(): the one-time allocation + synchronisation of the library (tile-counter ring, TMA encoder), on the
+    current device. Called once before the first GEMM so that no op of the hot loop allocates or synchronises."""
+    global _INITED
+    if not _INITED:
+        check(lib().llark_init(), "llark_init")
+        _INITED = True
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -47,6 +59,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_
     leading dimension = last-dim stride unless lda/ldb given. bf16 inputs use kind::f16, fp32 inputs kind::tf32.
     """
     _req(a), _req(b)
+    if not _INITED:
+        init()
     in_fp32 = a.dtype == torch.float32
     if a.dtype != b.dtype or a.dtype not in (BF16, torch.float32):
         raise TypeError("gemm inputs must both be bf16 or both fp32")
@@ -378,3 +392,58 @@ def jb_pool(acts, T_valid, frame):
     out = torch.empty((T_valid // frame, W), device=acts.device, dtype=torch.float32)
     check(lib().llark_jb_pool(_p(acts), _p(out), T_valid, W, frame, _stream()), "jb_pool")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ fp32 verification path
+def _f32(t):
+    return _req(t, torch.float32)
+
+
+def v32_split_tf32(x):
+    x = _f32(x).contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(lib().llark_v32_split_tf32(_p(x), _p(hi), _p(lo), x.numel(), _stream()), "v32_split_tf32")
+    return hi, lo
+
+
+def v32_embed_splice_fwd(ids, table, audio, audio_off, frames, start_pos, out):
+    B, S = ids.shape
+    H = table.shape[1]
+    check(lib().llark_v32_embed_splice_fwd(_p(ids), _p(_f32(table)), _p(audio), _p(audio_off), _p(frames), _p(start_pos),
+                                           _p(_f32(out)), B, S, H, table.shape[0], _stream()), "v32_embed_splice_fwd")
+    return out
+
+
+def v32_rmsnorm_fwd(x, w, eps):
+    rows, H = x.shape
+    y = torch.empty_like(_f32(x))
+    check(lib().llark_v32_rmsnorm_fwd(_p(x), _p(_f32(w)), _p(y), rows, H, eps, _stream()), "v32_rmsnorm_fwd")
+    return y
+
+
+def v32_rope_(qkv, cos_t, sin_t, S, n_rot_heads, D):
+    check(lib().llark_v32_rope(_p(_f32(qkv)), _p(_f32(cos_t)), _p(_f32(sin_t)), qkv.shape[0], S, n_rot_heads, D,
+                               qkv.stride(0), _stream()), "v32_rope")
+    return qkv
+
+
+def v32_swiglu_fwd(gu):
+    rows, I2 = gu.shape
+    act = torch.empty((rows, I2 // 2), device=gu.device, dtype=torch.float32)
+    check(lib().llark_v32_swiglu_fwd(_p(_f32(gu)), _p(act), rows, I2 // 2, _stream()), "v32_swiglu_fwd")
+    return act
+
+
+def v32_attn_fwd(qkv, key_mask, B, S, n_heads, head_dim):
+    out = torch.empty((B * S, n_heads * head_dim), device=qkv.device, dtype=torch.float32)
+    check(lib().llark_v32_attn_fwd(_p(_f32(qkv)), _p(key_mask), _p(out), B, S, n_heads, head_dim,
+                                   1.0 / math.sqrt(head_dim), _stream()), "v32_attn_fwd")
+    return out
+
+
+def v32_ce_fwd(logits, V, labels, B, S):
+    row_loss = torch.empty(B * S, device=logits.device, dtype=torch.float32)
+    loss_out = torch.empty(2, device=logits.device, dtype=torch.float32)
+    check(lib().llark_v32_ce_fwd(_p(_f32(logits)), logits.stride(0), V, _p(labels), B, S, _p(row_loss), _p(loss_out),
+                                 _stream()), "v32_ce_fwd")
+    return loss_out[0]

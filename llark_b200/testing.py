@@ -5,7 +5,7 @@ import torch
 BF16 = torch.bfloat16
 
 
-def build_model(cfg, params, detach_text=True, freeze_lm_head=True):
+def build_model(cfg, params, detach_text=True, freeze_lm_head=True, dtype=BF16):
     from llark_b200.models.llamav2 import WrappedLlamav2Config, WrappedLlamav2ForCausalLM
 
     hf = WrappedLlamav2Config(hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
@@ -21,7 +21,7 @@ def build_model(cfg, params, detach_text=True, freeze_lm_head=True):
     aec.use_audio_start_end = True
     aec.audio_start_token, aec.audio_end_token, aec.audio_patch_token = (
         cfg.audio_start_token, cfg.audio_end_token, cfg.audio_patch_token)
-    model.to(device="cuda", dtype=BF16)
+    model.to(device="cuda", dtype=dtype)
     if freeze_lm_head:
         for p in model.get_output_embeddings().parameters():
             p.requires_grad = False
