@@ -434,7 +434,7 @@ def jukebox_measure(precision="bf16", batch=8, steps=3, warmup=1, depth=36, objs
         z = ops.jb_vq_encode(lat, vqvae.w["codebook"])
         e[2].record()
         top_prior.prior.only_encode = True
-        acts = top_prior.prior.forward(z, None, None, None, False)
+        acts = top_prior.prior.forward(z, *top_prior.default_cond(), None, False)
         e[3].record()
         pooled = jm.pool_batch(acts, cfg.n_ctx, 34)
         e[4].record()

@@ -234,6 +234,10 @@ int llark_quick_gelu(const float* x, float* y, long long n, cudaStream_t stream)
 int llark_add3(const float* a, const float* b, const float* c, float* out, long long n, cudaStream_t stream);
 /* AvgPool1d(frame, stride frame, floor) over time: acts [T, W] -> out [T/frame, W] (jukebox/main.py:113-130). */
 int llark_jb_pool(const float* acts, float* out, int T_valid, int W, int frame, cudaStream_t stream);
+/* Timing conditioning x_cond of the top-level prior (upstream LabelConditioner's pos_emb, reached from
+ * jukebox/main.py:93): out[t,:] = (total_row + abs_table[abs_bins[t],:]) + rel_table[rel_bins[t],:], fp32 [T, W]. */
+int llark_jb_label_cond(const float* total_row, const float* abs_table, const float* rel_table, const int* abs_bins,
+                        const int* rel_bins, float* out, int T, int W, cudaStream_t stream);
 /* the same pool over N clips in one launch: acts [N, clip_stride/W rows, W], out [N, T_valid/frame, W] */
 int llark_jb_pool_batched(const float* acts, float* out, int N, long long clip_stride, int T_valid, int W, int frame,
                           cudaStream_t stream);

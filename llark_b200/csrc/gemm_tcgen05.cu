@@ -61,6 +61,7 @@ struct GemmParams {
     // fused epilogue (LlarkGemmEpilogue): 0 none, 1 quick-GELU, 2 RoPE on the first epi_i1 columns (head_dim 128,
     // position = row % epi_i0, epi_a / epi_b = cos / sin bf16 [S,128]), 3 SwiGLU backward (epi_a = gu bf16 [M, epi_ld]:
     // gate | up halves N apart; C receives dgate at column c and dup at column N + c)
+    int staged;      // 1 = staged (coalesced) epilogue, 0 = direct row-per-thread stores (see epilogue_dispatch)
     int epi;
     const void* epi_a;
     const void* epi_b;
@@ -468,12 +469,15 @@ __device__ __forceinline__ void epi_staged_bf16(const GemmParams& p, long long r
 }
 
 // Epilogue of one 128 x 256 accumulator tile for the warp owning TMEM lanes [32 ew, 32 ew + 32): rows row0 .. row0 + 31.
-// The RoPE columns of a fused-QKV projection keep the row-per-thread path (rotation partners are 64 columns apart);
-// everything else is staged. debug bit 64 = the old direct path everywhere (A/B measurements).
+// The RoPE columns of a fused-QKV projection keep the row-per-thread path (rotation partners are 64 columns apart).
+// p.staged (chosen on the host, llark_gemm_ex) selects the staged path where the epilogue is the longer leg: fp32 output
+// and the SwiGLU backward. Plain bf16 output stays direct: its epilogue already hides behind the next tile's MMAs, and
+// the staging patch's extra 256 KB of shared-memory traffic per tile slows the operand pipeline by 3-4 % (same-box A/B,
+// profiles/r2c_epilogue_ab.md).
 template <int EPI>
 __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, long long row0, int lane, int ncol0, uint32_t taddr,
                                                   float* stg) {
-    if ((EPI == 2 && ncol0 < p.epi_i1) || (p.debug & 64)) {
+    if ((EPI == 2 && ncol0 < p.epi_i1) || !p.staged) {
         const long long row = row0 + lane;
         epilogue_tile<EPI>(p, row, row < p.M, ncol0, taddr);
         return;
@@ -1251,6 +1255,14 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
     p.a_tma4 = a4 ? use4 : 0;
     p.b_tma4 = b4 ? use4 : 0;
     p.epi = ep ? ep->kind : 0;
+    {
+        static int mode = -1;  // LLARK_GEMM_EPILOGUE = auto (default) | staged | direct
+        if (mode < 0) {
+            const char* e = getenv("LLARK_GEMM_EPILOGUE");
+            mode = (e && e[0] == 's') ? 1 : ((e && e[0] == 'd') ? 2 : 0);
+        }
+        p.staged = mode == 1 ? 1 : (mode == 2 ? 0 : ((c_fp32 || p.epi == LLARK_EPI_SWIGLU_BWD) ? 1 : 0));
+    }
     p.epi_a = ep ? ep->a : nullptr;
     p.epi_b = ep ? ep->b : nullptr;
     p.epi_ld = ep ? ep->ld : 0;

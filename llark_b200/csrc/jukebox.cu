@@ -638,6 +638,17 @@ __global__ void jb_pool_kernel(const float* __restrict__ acts, float* __restrict
         }
     }
 }
+// Timing conditioning of the top-level prior (LabelConditioner.forward -> pos_emb, jukebox/main.py:93):
+// out[t, :] = (total_row + abs_table[abs_bins[t], :]) + rel_table[rel_bins[t], :] -- the reference's order of additions.
+__global__ void jb_label_cond_kernel(const float* __restrict__ total_row, const float* __restrict__ abs_table,
+                                     const float* __restrict__ rel_table, const int* __restrict__ abs_bins,
+                                     const int* __restrict__ rel_bins, float* __restrict__ out, int W) {
+    const int t = blockIdx.x;
+    const float* a = abs_table + (long long)abs_bins[t] * W;
+    const float* r = rel_table + (long long)rel_bins[t] * W;
+    float* o = out + (long long)t * W;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) o[c] = (total_row[c] + a[c]) + r[c];
+}
 // colsum over rows of a bf16 [rows, H] matrix -> bf16 [H] (bias gradient), fp32 accumulate.
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows,
                                    int H, int accumulate) {
@@ -808,6 +819,12 @@ extern "C" int llark_jb_pool_batched(const float* acts, float* out, int N, long 
 }
 extern "C" int llark_jb_pool(const float* acts, float* out, int T_valid, int W, int frame, cudaStream_t st) {
     return llark_jb_pool_batched(acts, out, 1, 0, T_valid, W, frame, st);
+}
+extern "C" int llark_jb_label_cond(const float* total_row, const float* abs_table, const float* rel_table,
+                                   const int* abs_bins, const int* rel_bins, float* out, int T, int W, cudaStream_t st) {
+    if (T <= 0 || W <= 0) return LLARK_EINVAL;
+    jb_label_cond_kernel<<<T, 256, 0, st>>>(total_row, abs_table, rel_table, abs_bins, rel_bins, out, W);
+    return jb_check();
 }
 extern "C" int llark_colsum(const void* x, void* out, long long rows, int H, int accumulate, cudaStream_t st) {
     if (rows <= 0 || H <= 0) return LLARK_EINVAL;

@@ -84,7 +84,8 @@ def get_z(audio, vqvae):
 
 
 def get_cond(hps, top_prior):
-    """jukebox/main.py:71-98: conditioning for the fixed metas (artist/genre "unknown", 62 s, offset 0)."""
+    """jukebox/main.py:71-98: conditioning for the fixed metas (artist/genre "unknown", 62 s, offset 0), computed for
+    hps.n_samples label rows of which row 0 is kept."""
     sample_length_in_seconds = 62
     hps.sample_length = (int(sample_length_in_seconds * hps.sr) // top_prior.raw_to_tokens) * top_prior.raw_to_tokens
     metas = [dict(artist="unknown", genre="unknown", total_length=hps.sample_length, offset=0,
@@ -157,7 +158,8 @@ def embed_batch(waveforms, vqvae, top_prior, pool_frames_per_second=10):
     w = w[:, :expected].cuda()
     z = vqvae.encode(w[:, :, None])[-1]
     top_prior.prior.only_encode = True
-    acts = top_prior.prior.forward(z[:, : cfg.n_ctx], x_cond=None, y_cond=None, encoder_kv=None, fp16=False)
+    x_cond, y_cond = top_prior.default_cond()  # the fixed metas of get_cond, computed once and cached
+    acts = top_prior.prior.forward(z[:, : cfg.n_ctx], x_cond=x_cond, y_cond=y_cond, encoder_kv=None, fp16=False)
     valid = min(latent_len, cfg.n_ctx)
     frame_len = floor((cfg.n_ctx / (expected / JUKEBOX_SAMPLE_RATE)) / pool_frames_per_second)
     return pool_batch(acts, valid, frame_len)
@@ -169,21 +171,44 @@ def pool_batch(acts, valid, frame_len):
     return ops.jb_pool_batched(acts.float().contiguous(), valid, frame_len)
 
 
-def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0):
-    """jukebox/main.py:176-200 -> (hps, vqvae, top_prior). No Jukebox checkpoint is reachable offline: `state`
-    = (vqvae_state, prior_state) dicts supplies weights, otherwise seeded random weights of the upstream shapes
-    (prior_depth 36) are created. `precision`: "tf32" (fp32 storage, parity mode) or "bf16"."""
+def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0, vqvae_checkpoint=None, prior_checkpoint=None,
+               artist_ids=None, genre_ids=None):
+    """jukebox/main.py:176-200 -> (hps, vqvae, top_prior): the VQ-VAE built for sample_length 1048576 and the top-level
+    prior with prior_depth forced to 36 (:197). Weights, in order of preference:
+      * `vqvae_checkpoint` / `prior_checkpoint`: upstream's vqvae.pth.tar / prior_level_2.pth.tar, read with the name maps
+        of model.py and loaded NON-STRICTLY like the reference's patched restore_model (make_models.py.patch:7-8): of the
+        72 transformer blocks in the file the first 36 are used, every other extra tensor is ignored;
+      * `state` = (vqvae_state, prior_state) dicts in this package's names;
+      * otherwise seeded random weights of the upstream shapes (no Jukebox checkpoint is reachable offline).
+    `precision`: "tf32" (fp32 storage, parity mode) or "bf16"."""
     from types import SimpleNamespace
+
+    from llark_b200.jukebox.model import (load_upstream_state, prior_key_map, random_label_state, vqvae_key_map)
 
     if model != "5b":
         raise NotImplementedError("LLark uses the 5b prior")
     cfg = cfg or JukeboxConfig()
     hps = SimpleNamespace(sr=JUKEBOX_SAMPLE_RATE, n_samples=8, name="samples", levels=3,
                           hop_fraction=[0.5, 0.5, 0.125], sample_length=cfg.sample_length)
-    vq_state, prior_state = state if state is not None else (random_vqvae_state(cfg, seed),
-                                                             random_prior_state(cfg, seed + 1, device="cuda"))
+    if vqvae_checkpoint is not None or prior_checkpoint is not None:
+        if vqvae_checkpoint is None or prior_checkpoint is None:
+            raise ValueError("pass both vqvae_checkpoint and prior_checkpoint")
+        vq_state, miss_v = load_upstream_state(vqvae_checkpoint, vqvae_key_map(cfg))
+        prior_state, miss_p = load_upstream_state(prior_checkpoint, prior_key_map(cfg))
+        if miss_v or miss_p:  # strict=False: report, do not raise (what torch's non-strict load returns as missing_keys)
+            logging.warning(f"tensors missing from the checkpoints (left uninitialised would be wrong: raising): "
+                            f"{(miss_v + miss_p)[:8]}{' ...' if len(miss_v + miss_p) > 8 else ''}")
+            raise KeyError(f"{len(miss_v + miss_p)} tensors of the 36-block front end are not in the checkpoints")
+    elif state is not None:
+        vq_state, prior_state = state
+    else:
+        vq_state = random_vqvae_state(cfg, seed)
+        prior_state = random_prior_state(cfg, seed + 1, device="cuda")
+        prior_state.update(random_label_state(cfg, seed=seed + 2, device="cuda"))
+        prior_state.pop("x_cond", None)  # conditioning now comes from the label tables (get_cond)
+        prior_state.pop("y_cond", None)
     vqvae = JukeboxVQVAE(cfg, vq_state)
-    top_prior = JukeboxTopPrior(cfg, prior_state, precision=precision)
+    top_prior = JukeboxTopPrior(cfg, prior_state, precision=precision, artist_ids=artist_ids, genre_ids=genre_ids)
     return hps, vqvae, top_prior
 
 

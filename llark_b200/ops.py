@@ -376,6 +376,16 @@ def add3(a, b, c=None, out=None):
     return out
 
 
+def jb_label_cond(total_row, abs_table, rel_table, abs_bins, rel_bins):
+    """x_cond [T, W] = (total_row + abs_table[abs_bins]) + rel_table[rel_bins] (fp32 tables, int32 bins on the device)."""
+    T, W = abs_bins.numel(), abs_table.shape[1]
+    out = torch.empty((T, W), device=abs_table.device, dtype=torch.float32)
+    check(lib().llark_jb_label_cond(_p(_req(total_row, torch.float32)), _p(_req(abs_table, torch.float32)),
+                                    _p(_req(rel_table, torch.float32)), _p(_req(abs_bins, torch.int32)),
+                                    _p(_req(rel_bins, torch.int32)), _p(out), T, W, _stream()), "jb_label_cond")
+    return out
+
+
 def jb_pool_batched(acts, T_valid, frame):
     """acts fp32 [N, T, W] (contiguous) -> [N, T_valid // frame, W]: windowed mean over time of every clip, one launch."""
     _req(acts, torch.float32)

@@ -383,6 +383,10 @@ def jb_pool(acts, T_valid, frame):
     return acts[: n * frame].view(n, frame, -1).mean(1)
 
 
+def jb_label_cond(total_row, abs_table, rel_table, abs_bins, rel_bins):
+    return (total_row[None] + abs_table[abs_bins.long()]) + rel_table[rel_bins.long()]
+
+
 def jb_pool_batched(acts, T_valid, frame):
     n = T_valid // frame
     return acts[:, : n * frame].reshape(acts.shape[0], n, frame, -1).mean(2)

@@ -380,7 +380,9 @@ def test_embed_splice_fwd_bwd_and_flags():
         if p >= 0:
             ref[b, p + 1: p + 1 + F] = audio[b * F: (b + 1) * F]
     assert torch.equal(out, ref)
-    # backward, detach_text path: only marker rows + audio rows
+    # backward, detach_text path: samples WITH an audio segment give gradient to the marker rows + audio rows only; the
+    # sample without <audio_start> keeps the reference's undetached embeddings (llamav2.py:162-208 never runs for it), so
+    # every one of its token rows receives gradient
     dout = torch.randn(B, S, H, device="cuda").to(BF16)
     daudio = torch.zeros(B * F, H, device="cuda", dtype=BF16)
     dtable = torch.zeros(V, H, device="cuda", dtype=BF16)
@@ -392,10 +394,12 @@ def test_embed_splice_fwd_bwd_and_flags():
             ref_da[b * F: (b + 1) * F] = dout[b, p + 1: p + 1 + F]
             ref_dt[start_id] += dout[b, p].float()
             ref_dt[end_id] += dout[b, p + F + 1].float()
+        else:
+            ref_dt.index_add_(0, ids[b], dout[b].float())
     assert torch.equal(daudio, ref_da)
     nz = dtable.float().abs().sum(-1).nonzero().flatten().tolist()
-    assert nz == [start_id, end_id]
-    assert _rel(dtable, ref_dt) < 1e-2
+    assert nz == sorted(set(ids[2].tolist()) | {start_id, end_id})
+    assert _rel(dtable, ref_dt) < 2e-2   # bf16 atomics: rows hit by several tokens round after every add
     # flag: end token misplaced / counts differ
     bad = ids.clone()
     bad[0, pos[0] + F + 1] = 5
