@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[2], named in `config.workload`): LLark Llama-2-7B + mm_projector training step on
 precomputed Jukebox embeddings -- random-init weights of the real architecture (H 4096, I 11008, 32 layers, 32
-heads, V 32004, projector 4800->4096), per-GPU micro-batch B (default 16) samples of S = 512 tokens (header + <audio_start> +
+heads, V 32004, projector 4800->4096), per-GPU micro-batch B (default 32) samples of S = 512 tokens (header + <audio_start> +
 240 audio frames + <audio_end> + 256 random text ids; labels on the last 128 tokens), bf16 weights / grads / Adam
 states as the reference trains (m2t/train.py:101-103), lm_head frozen, text-embedding rows detached. One "step" =
 forward + backward + gradient all-reduce (N > 1) + global-norm clip + AdamW on one micro-batch per GPU.
@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="llark", choices=["llark", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="per-GPU micro-batch (samples)")
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU micro-batch (samples)")
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers INVALIDATES the number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
@@ -503,6 +503,37 @@ def build_model(layers):
     return model
 
 
+def multi_gpu_checks(comm, opt, model, world, rank):
+    """Correctness bits of the N > 1 path, run once after the warm-up steps (outside the timed region):
+    (1) the library's bucket all-reduce (llark_grad_bucket_allreduce on the engine's communicator) against the exact
+    expected sum -- integer-valued bf16 data regenerated from every rank's seed, so the sum is exact -- and against
+    torch.distributed.all_reduce of a copy; (2) after the warm-up optimizer steps every rank holds bit-identical
+    parameters (what DDP guarantees: identical initial weights + identical averaged gradients)."""
+    import torch.distributed as dist
+
+    n = 1 << 24
+    def data(r):
+        g = torch.Generator(device="cuda").manual_seed(4242 + r)
+        return torch.randint(-8, 9, (n,), device="cuda", generator=g).to(torch.bfloat16)
+
+    mine = data(rank)
+    a, b = mine.clone(), mine.clone()
+    comm.allreduce_(a)
+    dist.all_reduce(b)
+    want = sum(data(r).float() for r in range(world))
+    torch.cuda.synchronize()
+    ok_sum = bool(torch.equal(a.float(), want)) and bool(torch.equal(a, b))
+    flat = model.engine.flat
+    digest = flat.params[: flat.n_train].view(torch.int16).to(torch.int64).sum().reshape(1)
+    all_d = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(all_d, digest)
+    same = all(int(d.item()) == int(all_d[0].item()) for d in all_d)
+    t = torch.tensor([int(ok_sum), int(same)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"bucket_allreduce_exact": bool(t[0].item()), "elements": n, "replicas_bit_identical_after_warmup":
+            bool(t[1].item()), "world": world}
+
+
 def measure_extras(args, model, opt, B, world, rank, timed):
     from llark_b200.jukebox import main as jm
 
@@ -644,6 +675,7 @@ def main():
         step_resident(i)
     torch.cuda.synchronize()
     model.check_audio_token_errors()
+    mg_checks = multi_gpu_checks(comm, opt, model, world, rank) if world > 1 else None
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res, prof = timed(step_resident, args.steps, profile=True)
     launches = (model.engine.launches + opt.launches) * args.steps
@@ -715,6 +747,8 @@ def main():
                      "flops_per_sample": fl["total"] / B, "gemm_by_shape": by_kind},
         "clocks": clocks,
     }
+    if mg_checks is not None:
+        line["multi_gpu_checks"] = mg_checks
     if extras:
         line.update(extras)
     if torch_base is not None:

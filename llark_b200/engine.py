@@ -544,10 +544,10 @@ class LlamaEngine:
             ops.rmsnorm_bwd(x, flat.pview(pfx + "input_layernorm.weight"), dxn1, rstd1, dx_mid, dx,
                             flat.gview(pfx + "input_layernorm.weight"), acc, ws_norm)
             n0 += 2
-            if self.grad_ready_hook is not None and l % self.comm_chunk_layers == 0:
+            if self.grad_ready_hook is not None and l in self._comm_slices(L):
                 # layers [l, hi) are final: their gradients form one contiguous slice of the bucket
                 lo_off = flat.offsets[f"model.layers.{l}.self_attn.q_proj.weight"][0]
-                hi_l = min(l + self.comm_chunk_layers, L)
+                hi_l = self._comm_slices(L)[l]
                 hi_off = (flat.offsets[f"model.layers.{hi_l}.self_attn.q_proj.weight"][0] if hi_l < L
                           else flat.offsets["model.norm.weight"][0])
                 if lo_off < flat.n_train and hi_off <= flat.n_train and hi_off > lo_off:
@@ -577,6 +577,22 @@ class LlamaEngine:
                 n0 += 1
         flat.attach_grads()
         self.launches = n0
+
+    def _comm_slices(self, L):
+        """{first layer of a slice: one past its last layer}. Slices are `comm_chunk_layers` layers wide, except that the
+        slice holding layers [0, chunk) -- final only when the backward is almost over, so its all-reduce cannot hide
+        behind any GEMM -- is split into single layers: the exposed tail is then one layer (0.4 GB at 7B) plus the
+        embedding / projector remainder instead of `chunk` layers (1.6 GB). LLARK_COMM_TAIL_SPLIT=0 restores equal slices."""
+        key = (L, self.comm_chunk_layers)
+        if getattr(self, "_slices_key", None) != key:
+            c = self.comm_chunk_layers
+            starts = set(range(0, L, c))
+            if os.environ.get("LLARK_COMM_TAIL_SPLIT", "1") != "0":
+                starts |= set(range(0, min(c, L)))
+            starts = sorted(starts)
+            self._slices = {a: (starts[i + 1] if i + 1 < len(starts) else L) for i, a in enumerate(starts)}
+            self._slices_key = key
+        return self._slices
 
     # ------------------------------------------------------------------------------------------ validation
     def check_flags(self):

@@ -172,7 +172,7 @@ def pool_batch(acts, valid, frame_len):
 
 
 def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0, vqvae_checkpoint=None, prior_checkpoint=None,
-               artist_ids=None, genre_ids=None):
+               artist_ids=None, genre_ids=None, device="cuda"):
     """jukebox/main.py:176-200 -> (hps, vqvae, top_prior): the VQ-VAE built for sample_length 1048576 and the top-level
     prior with prior_depth forced to 36 (:197). Weights, in order of preference:
       * `vqvae_checkpoint` / `prior_checkpoint`: upstream's vqvae.pth.tar / prior_level_2.pth.tar, read with the name maps
@@ -203,12 +203,13 @@ def load_model(model="5b", state=None, cfg=None, precision="tf32", seed=0, vqvae
         vq_state, prior_state = state
     else:
         vq_state = random_vqvae_state(cfg, seed)
-        prior_state = random_prior_state(cfg, seed + 1, device="cuda")
-        prior_state.update(random_label_state(cfg, seed=seed + 2, device="cuda"))
+        prior_state = random_prior_state(cfg, seed + 1, device=device)
+        prior_state.update(random_label_state(cfg, seed=seed + 2, device=device))
         prior_state.pop("x_cond", None)  # conditioning now comes from the label tables (get_cond)
         prior_state.pop("y_cond", None)
-    vqvae = JukeboxVQVAE(cfg, vq_state)
-    top_prior = JukeboxTopPrior(cfg, prior_state, precision=precision, artist_ids=artist_ids, genre_ids=genre_ids)
+    vqvae = JukeboxVQVAE(cfg, vq_state, device=device)
+    top_prior = JukeboxTopPrior(cfg, prior_state, device=device, precision=precision, artist_ids=artist_ids,
+                                genre_ids=genre_ids)
     return hps, vqvae, top_prior
 
 

@@ -64,7 +64,7 @@ def _model_and_data(rank_of_batch):
     from oracle import llama_oracle as lo
     from test_engine_host_cpu import _build
 
-    cfg = lo.LlamaCfg(num_layers=6)       # comm_chunk_layers = 4 -> two overlap slices + the remainder
+    cfg = lo.LlamaCfg(num_layers=6)       # comm_chunk_layers = 4 -> slices [4,6) and, tail split, [3,4) [2,3) [1,2) [0,1)
     model = _build(cfg, lo.init_params(cfg, seed=0))
     for p in model.get_output_embeddings().parameters():
         p.requires_grad = False
@@ -128,7 +128,7 @@ def test_world2_trainer_overlapped_bucket_allreduce(tmp_path):
     assert per_step * STEPS == len(log0) and per_step >= 3
     for s in range(STEPS):
         calls = log0[s * per_step:(s + 1) * per_step]
-        assert sum(1 for c in calls if c[2]) == 2                        # two overlap slices on the side stream
+        assert sum(1 for c in calls if c[2]) == 5                        # overlap slices on the side stream (tail split)
         spans = sorted((a, a + n) for a, n, _ in calls)
         assert spans[0][0] == 0 and spans[-1][1] == n_train
         assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))

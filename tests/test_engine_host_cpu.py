@@ -268,7 +268,7 @@ def test_backward_announces_final_layer_gradients_in_reverse_order(cpu_engine):
         model(**batch).loss.backward()
         flat = eng.flat
         spans = [(a, b) for a, b, _ in calls]
-        assert spans == sorted(spans, reverse=True) and len(spans) == 3
+        assert spans == sorted(spans, reverse=True) and len(spans) == 4   # [4,5) [2,4) + the tail split [1,2) [0,1)
         assert spans[-1][0] == flat.offsets["model.layers.0.self_attn.q_proj.weight"][0]
         assert spans[0][1] == flat.offsets["model.norm.weight"][0]
         assert all(spans[i][0] == spans[i + 1][1] for i in range(len(spans) - 1))

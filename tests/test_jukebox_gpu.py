@@ -152,3 +152,30 @@ def test_get_acts_from_file_end_to_end_tiny():
         jm.get_z(np.zeros(10, dtype=np.float32), vqvae)
     full = jm.get_acts_from_file(stereo, hps, vqvae, top_prior, meanpool=True, pool_frames_per_second=0)
     assert full.shape == (ocfg.prior_width,)
+
+
+def test_label_conditioning_on_gpu_matches_oracle_and_feeds_the_prior():
+    """J4 on the GPU: get_cond through llark_jb_label_cond (bins on the host, table arithmetic in the kernel) is bit-equal
+    to the oracle's LabelConditioner, embed_batch / get_acts_from_file use it (no ready-made x_cond / y_cond constants in
+    the state), and the whole front end still agrees with the oracle run on those conditioning tensors."""
+    jo, ocfg, cfg = _cfgs()
+    from types import SimpleNamespace
+
+    from llark_b200.jukebox import main as jm
+
+    vq, pp = jo.init_vqvae_params(ocfg, 0), jo.init_prior_params(ocfg, 1)
+    pp.pop("x_cond"), pp.pop("y_cond")
+    tables = jo.init_label_params(ocfg, jo.LabelCfg(), seed=5)
+    hps, vqvae, top_prior = jm.load_model("5b", state=(vq, {**pp, **tables}), cfg=cfg)
+    assert top_prior.has_label_conditioner
+    x_cond, y_cond = jm.get_cond(SimpleNamespace(sr=44100, n_samples=8), top_prior)
+    want_x, want_y = jo.get_cond(tables, ocfg, jo.LabelCfg())
+    assert torch.equal(x_cond.cpu(), want_x) and torch.equal(y_cond.cpu(), want_y)
+    g = torch.Generator().manual_seed(3)
+    wav = (torch.rand(2, ocfg.sample_length, generator=g) * 2 - 1)
+    got = jm.embed_batch(wav, vqvae, top_prior, pool_frames_per_second=10).cpu()
+    opp = {**pp, "x_cond": want_x[0], "y_cond": want_y[0, 0]}
+    for i in range(2):
+        ref = jo.get_acts(wav[i], vq, opp, ocfg, meanpool=True, pool_frames_per_second=10)
+        per_frame = (got[i] - ref).norm(dim=1) / ref.norm(dim=1)
+        assert got[i].shape == ref.shape and (per_frame < 2e-2).float().mean().item() > 0.9

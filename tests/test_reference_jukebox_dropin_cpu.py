@@ -37,8 +37,12 @@ def test_reference_jukebox_main_runs_over_llark_objects(tmp_path, monkeypatch):
 
     cfg = jmodel.JukeboxConfig(prior_depth=1)
     vqvae = jmodel.JukeboxVQVAE(cfg, jmodel.random_vqvae_state(cfg, seed=0), device="cpu")
-    top_prior = jmodel.JukeboxTopPrior(cfg, jmodel.random_prior_state(cfg, seed=1, device="cpu"), device="cpu",
-                                       precision="tf32")
+    # label tables instead of ready-made constants: the reference's get_cond (jukebox/main.py:71-98) then drives the
+    # labeller -> get_y -> get_cond protocol for real
+    state = jmodel.random_prior_state(cfg, seed=1, device="cpu")
+    state.pop("x_cond"), state.pop("y_cond")
+    state.update(jmodel.random_label_state(cfg, seed=2, device="cpu"))
+    top_prior = jmodel.JukeboxTopPrior(cfg, state, device="cpu", precision="tf32")
     hps = SimpleNamespace(sr=44100, n_samples=8, name="samples", levels=3, hop_fraction=[0.5, 0.5, 0.125])
 
     rng = np.random.default_rng(0)

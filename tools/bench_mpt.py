@@ -1,9 +1,12 @@
 """BASELINE configs[4]: CLAP + MPT-1B training step -- one [1, 512] CLAP embedding per sample
 spliced into a 256-token sequence, MPT-1B dims (m2t/llava/model/mpt/configuration_mpt.py:30-36: d_model 2048, 16 heads,
 24 layers, expansion 4, vocab 50368; ALiBi, q/k LayerNorm, no biases, tied head), bf16, fwd + bwd + clip + AdamW.
-STAGED like the kernels it drives (llark_b200/csrc/mpt_ops.cu, attention_tc_alibi.cu): it has not run on a B200 yet.
+First run on a B200 in round 2 (profiles/r2a_bench_mpt.json). Under torchrun it is the data-parallel step on N GPUs
+(configs[4] names 2 x B200): one rank per GPU, the flat-bucket NCCL all-reduce overlapped with backward as in bench.py.
 
     python tools/bench_mpt.py [--batch 32] [--steps 5] [--warmup 3] [--layers 24]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
+        tools/bench_mpt.py
     python tools/bench_mpt.py --cpu-standin --layers 1 --d-model 256 --heads 2 --vocab 512 --batch 2
         (no GPU: exercises this script's own logic with the test-only PyTorch stand-in for the ops; prints no rates)
 
@@ -112,10 +115,21 @@ def main():
     from llark_b200 import ops
     from llark_b200.optim import LlarkAdamW
 
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    comm = None
+    if world > 1 and device == "cuda":
+        import torch.distributed as dist
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from llark_b200.comm import GradComm
+
+        comm = GradComm.from_torch_distributed()
     torch.manual_seed(1234)
     model = build_model(a, device)
-    opt = LlarkAdamW(model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0)
-    host = [synth_batch(a, 1000 + i) for i in range(4)]
+    opt = LlarkAdamW(model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, comm=comm)
+    host = [synth_batch(a, 1000 + rank + world * i) for i in range(4)]
     if device == "cuda":
         pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
         resident = [{k: v.cuda() for k, v in b.items()} for b in host]
@@ -144,8 +158,15 @@ def main():
                           / a.batch}))
         return
 
-    def timed(fn, steps, profile=False):
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if profile:
             ops.GEMM_PROFILE = []
@@ -153,9 +174,16 @@ def main():
         for i in range(steps):
             fn(i)
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
         prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-        return e0.elapsed_time(e1), prof
+        ms = e0.elapsed_time(e1)
+        if world > 1:  # device time, max over ranks
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, prof
 
     for i in range(a.warmup):
         step_resident(i)
@@ -166,14 +194,22 @@ def main():
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, a.steps)
     fl = step_flops(a.batch, SEQ, a.d_model, a.layers, a.vocab + 4, 4)
-    n = a.batch * a.steps
+    n = a.batch * a.steps * world
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     print(json.dumps({
-        "workload": f"configs[4]: CLAP [1,512] + MPT-1B training step, seq {SEQ}, bf16, batch {a.batch}, layers {a.layers}",
+        "workload": f"configs[4]: CLAP [1,512] + MPT-1B training step, seq {SEQ}, bf16, per-GPU batch {a.batch}, "
+                    f"layers {a.layers}, dp{world}", "n_gpus": world,
         "samples_per_s": n / (ms_res / 1000.0), "ms_per_step": ms_res / a.steps,
         "e2e": {"samples_per_s": n / (ms_e2e / 1000.0), "ms_per_step": ms_e2e / a.steps,
                 "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host[0].values()),
                 "d2h_bytes_per_step": 4},
-        "step_tflops_algorithmic": fl["total"] * a.steps / (ms_res / 1000.0) / 1e12,
+        "step_tflops_algorithmic_per_gpu": fl["total"] * a.steps / (ms_res / 1000.0) / 1e12,
         "flops_per_sample": fl["total"] / a.batch,
         "gemm": {"tflops": gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms else None,
                  "share_of_step": gemm_ms / ms_res if ms_res else None, "launches": len(prof)},
