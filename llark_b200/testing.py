@@ -34,3 +34,14 @@ def to_cuda(batch):
     return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
 
 
+
+
+# ---- measured parity errors: every tolerance check of the GPU parity tests goes through check_close, which records the
+# measured value next to its bound; tests/conftest.py writes the table to gpurun_out/parity_measured.txt at session end
+PARITY_LOG = []
+
+
+def check_close(name, measured, tol):
+    measured = float(measured)
+    PARITY_LOG.append((name, measured, float(tol)))
+    assert measured < tol, f"{name}: measured {measured:.4e} >= bound {tol:.1e}"

@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+from llark_b200.testing import check_close  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -39,7 +41,7 @@ def test_conv_encoder_and_vq_match_oracle():
     m = JukeboxVQVAE(cfg, vq)
     lat = m.encode_top_latents(audio[:, None, :].cuda().contiguous())
     assert lat.shape == lat_o.shape
-    assert _rel(lat, lat_o) < 1e-4
+    check_close("test_conv_encoder_and_vq_match_oracle:_rel_lat_lat_o_", _rel(lat, lat_o), 1e-4)
     codes = m.encode(audio[:, :, None].cuda())[-1].cpu()
     assert codes.dtype == torch.int64 and codes.shape == codes_o.shape
     neq = (codes != codes_o).flatten().nonzero().flatten()
@@ -86,7 +88,7 @@ def test_sparse_attention_real_head_shape(pattern):
     ref = jo.factored_attention(qkv, cfg, pattern)
     q = qkv.view(2048, -1).cuda().contiguous()
     out = ops.jb_sparse_attn(q, 1, 2048, 8, 150, 64, pattern, exact=True)  # fp32 SIMT kernel
-    assert _rel(out.view(1, 2048, -1), ref) < 1e-4
+    check_close("test_sparse_attention_real_head_shape:_rel_out_view_1_2048_1_ref_", _rel(out.view(1, 2048, -1), ref), 1e-4)
     # tensor-core kernel: operands rounded to TF32 (10-bit mantissa), fp32 accumulate -> 2e-3; bf16 output adds 2^-9
     out_tc = ops.jb_sparse_attn(q, 1, 2048, 8, 150, 64, pattern)
     assert out_tc.dtype == torch.float32 and _rel(out_tc.view(1, 2048, -1), ref) < 2e-3
@@ -109,7 +111,7 @@ def test_sparse_attention_tc_full_geometry(pattern):
     qkv = torch.randn(2 * 8192, 3600, device="cuda", generator=g)
     ref = ops.jb_sparse_attn(qkv, 2, 8192, 8, 150, 64, pattern, exact=True)
     got = ops.jb_sparse_attn(qkv, 2, 8192, 8, 150, 64, pattern)
-    assert _rel(got, ref) < 2e-3
+    check_close("test_sparse_attention_tc_full_geometry:_rel_got_ref_", _rel(got, ref), 2e-3)
 
 
 def test_pool_matches_reference_golden():

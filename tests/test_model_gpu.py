@@ -8,6 +8,8 @@ import os
 import pytest
 import torch
 
+from llark_b200.testing import check_close  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 BF16 = torch.bfloat16
@@ -42,7 +44,7 @@ def test_forward_backward_matches_reference_golden(gold, detach):
     assert abs(out.loss.item() - ref16["loss"].item()) < 2e-3 * ref16["loss"].item()
     valid = batch["attention_mask"]
     lg = out.logits.float().cpu()[valid]
-    assert _rel(lg, ref16["logits"].float()[valid]) < 2e-2
+    check_close("test_forward_backward_matches_reference_golden:_rel_lg_ref16_logits_float_valid_", _rel(lg, ref16["logits"].float()[valid]), 2e-2)
     err_mine = _rel(lg, ref32["logits"][valid])
     err_ref = _rel(ref16["logits"].float()[valid], ref32["logits"][valid])
     assert err_mine < 1.5 * err_ref + 1e-3, (err_mine, err_ref)
@@ -55,7 +57,7 @@ def test_forward_backward_matches_reference_golden(gold, detach):
         assert g is not None, n
         assert abs(g.float().norm().item() - entry["norm"]) <= 5e-2 * max(entry["norm"], 1e-6), n
         if "full" in entry:
-            assert _rel(g.float(), entry["full"].float()) < 4e-2, n
+            check_close(f"test_forward_backward_matches_reference_golden:_rel_g_float_entry_full_float_:{n}", _rel(g.float(), entry["full"].float()), 4e-2)
         if "nonzero_rows" in entry:
             rows = g.float().abs().sum(-1).nonzero().flatten().tolist()
             assert rows == entry["nonzero_rows"], n
@@ -92,25 +94,25 @@ def test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation():
     out.loss.backward()
     assert abs(out.loss.item() - loss_o.item()) < 3e-3 * loss_o.item()
     valid = batch["attention_mask"]
-    assert _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]) < 2e-2
+    check_close("test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_out_logits_float_cpu_valid_logits_o", _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]), 2e-2)
     named = dict(model.named_parameters())
     for n, go in grads_o.items():
         if go is None:
             assert named[n].grad is None
             continue
-        assert _rel(named[n].grad.float(), go.float()) < 6e-2, n
+        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_go_float_:{n}", _rel(named[n].grad.float(), go.float()), 6e-2)
     # second micro-batch accumulates in place (wgrad epilogue R = C): grads double
     g1 = {n: p.grad.float().clone() for n, p in named.items() if p.grad is not None}
     out2 = model(**cb)
     out2.loss.backward()
     for n, g in g1.items():
-        assert _rel(named[n].grad.float(), 2 * g) < 2e-2, n
+        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_2_g_:{n}", _rel(named[n].grad.float(), 2 * g), 2e-2)
     # zero_grad(set_to_none) -> overwrite mode again
     model.zero_grad(set_to_none=True)
     out3 = model(**cb)
     out3.loss.backward()
     for n, g in g1.items():
-        assert _rel(named[n].grad.float(), g) < 1e-2, n
+        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_g_:{n}", _rel(named[n].grad.float(), g), 1e-2)
 
 
 def test_value_errors_and_no_grad_forward(gold):
@@ -164,11 +166,11 @@ def test_llama7b_layer_shapes_run():
                                                     detach_text=True)
     assert abs(out.loss.item() - loss_o.item()) < 3e-3 * loss_o.item()
     valid = batch["attention_mask"]
-    assert _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]) < 2e-2
+    check_close("test_llama7b_layer_shapes_run:_rel_out_logits_float_cpu_valid_logits_o", _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]), 2e-2)
     named = dict(model.named_parameters())
     for n in ("model.mm_projector.weight", "model.layers.0.mlp.down_proj.weight", "model.layers.0.self_attn.q_proj.weight",
               "model.norm.weight"):
-        assert _rel(named[n].grad.float(), grads_o[n].float()) < 6e-2, n
+        check_close(f"test_llama7b_layer_shapes_run:_rel_named_n_grad_float_grads_o_n_float_:{n}", _rel(named[n].grad.float(), grads_o[n].float()), 6e-2)
 
 
 def test_optimizer_step_then_backward_overwrites_stale_grads(gold):
@@ -199,7 +201,7 @@ def test_optimizer_step_then_backward_overwrites_stale_grads(gold):
     model(**batch).loss.backward()
     for n, p in model.named_parameters():
         if p.grad is not None:
-            assert _rel(p.grad.float(), 2 * g_a[n]) < 2e-2, n
+            check_close(f"test_optimizer_step_then_backward_overwrites_stale_grads:_rel_p_grad_float_2_g_a_n_:{n}", _rel(p.grad.float(), 2 * g_a[n]), 2e-2)
 
 
 def test_generate_greedy_decoding_without_cache():
@@ -326,7 +328,7 @@ def test_frozen_backbone_projector_only_training_on_gpu(gold):
     _, _, grads_o = lo.forward_backward({k: v.to(torch.bfloat16) for k, v in params.items()}, cfg, batch)
     named = dict(model.named_parameters())
     for n in ("model.mm_projector.weight", "model.mm_projector.bias", "model.embed_tokens.weight"):
-        assert _rel(named[n].grad.float(), grads_o[n].float()) < 6e-2, n
+        check_close(f"test_frozen_backbone_projector_only_training_on_gpu:_rel_named_n_grad_float_grads_o_n_float_:{n}", _rel(named[n].grad.float(), grads_o[n].float()), 6e-2)
     assert all(p.grad is None for n, p in named.items() if "layers" in n or n in ("model.norm.weight", "lm_head.weight"))
     l0 = out.loss.item()
     for _ in range(3):
@@ -336,7 +338,7 @@ def test_frozen_backbone_projector_only_training_on_gpu(gold):
         assert model(**_to_cuda(batch)).loss.item() < l0
 
 
-@pytest.mark.parametrize("gemm_mode,tol", [("3xtf32", 1e-3), ("tf32", 1e-2)])
+@pytest.mark.parametrize("gemm_mode,tol", [("3xtf32", 1e-3), ("tf32", 2e-3)])
 def test_fp32_verification_mode_meets_the_1e3_logit_criterion(gold, gemm_mode, tol, capsys):
     """north_star: "fp32 logits within 1e-3 relative" of the reference's own PyTorch path. LLARK_VERIFY=fp32 runs the forward
     with fp32 tensors end to end (3xTF32 products on the tcgen05 core + csrc/verify_fp32.cu) and is compared with the fp32

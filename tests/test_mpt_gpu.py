@@ -9,6 +9,8 @@ import sys
 import pytest
 import torch
 
+from llark_b200.testing import check_close  # noqa: E402
+
 sys.path.insert(0, os.path.dirname(__file__))
 BF16 = torch.bfloat16
 pytestmark = [pytest.mark.gpu]
@@ -44,21 +46,21 @@ def test_layernorm_forward_backward(rows, W, strided):
     ops.ln_fwd(xd[:, sl], wd, 1e-5, mean=mu, rstd=rs, out=y_full[:, sl])
     assert torch.allclose(mu.cpu(), mu_r, rtol=1e-4, atol=1e-4)
     assert torch.allclose(rs.cpu(), rs_r, rtol=1e-4, atol=1e-5)
-    assert _rel(y_full[:, sl].cpu(), y_r) < 4e-3
+    check_close("test_layernorm_forward_backward:_rel_y_full_sl_cpu_y_r_", _rel(y_full[:, sl].cpu(), y_r), 4e-3)
     if strided:   # neighbours of the view untouched
         assert y_full[:, :W].abs().sum().item() == 0 and y_full[:, 2 * W:].abs().sum().item() == 0
     dx_full = torch.zeros((rows, full_w), device="cuda", dtype=BF16)
     dw = torch.full((W,), 0.25, device="cuda", dtype=BF16)
     ops.ln_bwd(xd[:, sl], wd, dyd[:, sl], mu, rs, dresd, dx_full[:, sl], dw, True)
-    assert _rel(dx_full[:, sl].cpu(), dx_r) < 6e-3
-    assert _rel(dw.cpu(), dw_r) < 1e-2
+    check_close("test_layernorm_forward_backward:_rel_dx_full_sl_cpu_dx_r_", _rel(dx_full[:, sl].cpu(), dx_r), 6e-3)
+    check_close("test_layernorm_forward_backward:_rel_dw_cpu_dw_r_", _rel(dw.cpu(), dw_r), 1e-2)
     dw2 = torch.full((W,), 7.0, device="cuda", dtype=BF16)
     ops.ln_bwd(xd[:, sl], wd, dyd[:, sl], mu, rs, None, dx_full[:, sl], dw2, False)   # overwrite, no residual gradient
     dx_r2, dw_r2 = torch.empty((rows, W), dtype=BF16), torch.empty((W,), dtype=BF16)
     cpu_ops.ln_bwd(x_full[:, sl], w, dy_full[:, sl], mu_r, rs_r, None, dx_r2, dw_r2, False)
-    assert _rel(dx_full[:, sl].cpu(), dx_r2) < 6e-3 and _rel(dw2.cpu(), dw_r2) < 1e-2
+    check_close("test_layernorm_forward_backward:_rel_dx_full_sl_cpu_dx_r2_6e_3_and__rel_", _rel(dx_full[:, sl].cpu(), dx_r2) < 6e-3 and _rel(dw2.cpu(), dw_r2), 1e-2)
     ops.ln_bwd(xd[:, sl], wd, dyd[:, sl], mu, rs, None, dx_full[:, sl], None, False)   # dw not wanted
-    assert _rel(dx_full[:, sl].cpu(), dx_r2) < 6e-3
+    check_close("test_layernorm_forward_backward:_rel_dx_full_sl_cpu_dx_r2_", _rel(dx_full[:, sl].cpu(), dx_r2), 6e-3)
 
 
 @pytest.mark.parametrize("n", [8, 4096, 300 * 8192])
@@ -73,7 +75,7 @@ def test_exact_gelu_forward_backward(n):
     du = ops.gelu_bwd(u.cuda(), dh.cuda())
     h_r, du_r = cpu_ops.gelu_fwd(u), cpu_ops.gelu_bwd(u, dh)
     # same fp32 formula, one bf16 rounding: allow one ulp on a handful of elements
-    assert _rel(h.cpu(), h_r) < 3e-3 and _rel(du.cpu(), du_r) < 3e-3
+    check_close("test_exact_gelu_forward_backward:_rel_h_cpu_h_r_3e_3_and__rel_du_cpu_du_r", _rel(h.cpu(), h_r) < 3e-3 and _rel(du.cpu(), du_r), 3e-3)
     assert (h.cpu().float() - h_r.float()).abs().max().item() <= 2 ** -7 * h_r.float().abs().max().item()
 
 
@@ -96,7 +98,7 @@ def test_alibi_attention_forward_backward(B, S, NH, lens):
     dqkv_r = cpu_ops.attn_alibi_bwd(qkv, mask, o_r, dout, lse_r, B, S, NH, D, slopes)
     o, lse = ops.attn_alibi_fwd(qkv.cuda(), mask.cuda(), B, S, NH, D, slopes.cuda())
     valid = mask.bool().view(-1)
-    assert _rel(o.cpu()[valid], o_r[valid]) < 6e-3
+    check_close("test_alibi_attention_forward_backward:_rel_o_cpu_valid_o_r_valid_", _rel(o.cpu()[valid], o_r[valid]), 6e-3)
     lv = mask.bool()[:, None, :].expand(B, NH, S)
     assert (lse.cpu()[lv] - lse_r[lv]).abs().max().item() < 2e-2
     dqkv = ops.attn_alibi_bwd(qkv.cuda(), mask.cuda(), o, dout.cuda(), lse, B, S, NH, D, slopes.cuda())
@@ -104,11 +106,11 @@ def test_alibi_attention_forward_backward(B, S, NH, lens):
     dd[~valid] = 0   # rows of padded queries carry no loss in the engine; compare on what matters
     dqkv_r = cpu_ops.attn_alibi_bwd(qkv, mask, o_r, dd, lse_r, B, S, NH, D, slopes)
     dqkv_v = ops.attn_alibi_bwd(qkv.cuda(), mask.cuda(), o, dd.cuda(), lse, B, S, NH, D, slopes.cuda())
-    assert _rel(dqkv_v.cpu()[valid], dqkv_r[valid]) < 1.5e-2
+    check_close("test_alibi_attention_forward_backward:_rel_dqkv_v_cpu_valid_dqkv_r_valid_", _rel(dqkv_v.cpu()[valid], dqkv_r[valid]), 1.5e-2)
     # slope 0 reduces to the plain causal kernel (bit-identical code path apart from one FFMA per score)
     o0, lse0 = ops.attn_alibi_fwd(qkv.cuda(), mask.cuda(), B, S, NH, D, torch.zeros(NH, device="cuda"))
     o1, lse1 = ops.attn_fwd(qkv.cuda(), mask.cuda(), B, S, NH, D)
-    assert _rel(o0[valid.cuda()], o1[valid.cuda()]) < 1e-3
+    check_close("test_alibi_attention_forward_backward:_rel_o0_valid_cuda_o1_valid_cuda_", _rel(o0[valid.cuda()], o1[valid.cuda()]), 1e-3)
 
 
 @pytest.mark.parametrize("F_frames,detach", [(1, False), (4, True)])
@@ -130,8 +132,8 @@ def test_mpt_engine_step_matches_oracle_on_gpu(F_frames, detach):
     loss_o, logits_o, grads_o = mo.forward_backward(pb, cfg, batch, detach_text=detach, autocast_dtype=BF16)
     assert abs(out.loss.item() - loss_o.item()) < 3e-3 * loss_o.item()
     valid = batch["attention_mask"]
-    assert _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]) < 2e-2
+    check_close("test_mpt_engine_step_matches_oracle_on_gpu:_rel_out_logits_float_cpu_valid_logits_o", _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]), 2e-2)
     named = dict(model.named_parameters())
     for name, g_ref in grads_o.items():
         assert named[name].grad is not None, name
-        assert _rel(named[name].grad.cpu(), g_ref) < 6e-2, name
+        check_close(f"test_mpt_engine_step_matches_oracle_on_gpu:_rel_named_name_grad_cpu_g_ref_:{name}", _rel(named[name].grad.cpu(), g_ref), 6e-2)
