@@ -718,11 +718,23 @@ def main():
     fl = step_flops(B, args.layers)
     achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    traffic = None
+    # DRAM traffic of the GEMM kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu pass over the
+    # bench's OWN shapes (tools/gpu/r2_evidence.sh -> profiles/gemm_traffic.json, keyed like gemm_by_shape); `traffic` is
+    # the launch-weighted mean over this step's launches, `traffic_by_shape` carries each shape next to its algorithmic bytes
+    traffic, traffic_by_shape = None, None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        shapes = tj.get("by_shape") or {}
+        hit = {k: shapes[k] for k in by_kind if k in shapes}
+        if hit:
+            n_l = sum(by_kind[k]["launches"] for k in hit)
+            traffic = sum(by_kind[k]["launches"] * hit[k]["dram_bytes_per_launch"] for k in hit) / n_l
+            traffic_by_shape = {k: {"dram_bytes_per_launch": v["dram_bytes_per_launch"],
+                                    "algorithmic_bytes_per_launch": v["algorithmic_bytes_per_launch"],
+                                    "ratio": v["traffic_over_algorithmic"]} for k, v in hit.items()}
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -744,7 +756,8 @@ def main():
                      "peak_kind": f"{pk_kind} bf16_tflops_sustained", "gemm_launches_timed": n_gemm,
                      "gemm_share_of_step": gemm_ms / ms_res if ms_res else None,
                      "step_tflops_algorithmic": fl["total"] * world * args.steps / (ms_res / 1000.0) / 1e12 / world,
-                     "flops_per_sample": fl["total"] / B, "gemm_by_shape": by_kind},
+                     "flops_per_sample": fl["total"] / B, "gemm_by_shape": by_kind,
+                     "traffic_by_shape": traffic_by_shape},
         "clocks": clocks,
     }
     if mg_checks is not None:

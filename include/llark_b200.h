@@ -158,6 +158,12 @@ long long llark_attn_bwd_workspace(int B, int S, int n_heads);
 int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout, const float* lse,
                    void* dqkv, int B, int S, int n_heads, int head_dim, float scale, void* workspace,
                    cudaStream_t stream);
+/* llark_attn_bwd with the inverse rotary embedding of the dq | dk heads fused into the backward kernels' epilogues
+ * (rope_cos / rope_sin: bf16 [S, 128], position = row % S): dqkv is then the gradient of the PRE-RoPE QKV projection
+ * output, bit-identical to llark_attn_bwd followed by llark_rope(inverse = 1) -- one pass over dqkv less per layer. */
+int llark_attn_bwd_rope(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                        const float* lse, void* dqkv, int B, int S, int n_heads, int head_dim, float scale,
+                        const void* rope_cos, const void* rope_sin, void* workspace, cudaStream_t stream);
 
 /* Column sum of a bf16 [rows, H] matrix into bf16 [H] (+= if accumulate): the mm_projector bias gradient. */
 int llark_colsum(const void* x, void* out, long long rows, int H, int accumulate, cudaStream_t stream);

@@ -24,7 +24,7 @@ SYMBOLS = [
     "llark_jb_conv_k3", "llark_jb_vq_encode", "llark_layernorm_fwd", "llark_jb_embed_tokens", "llark_jb_sparse_attn",
     "llark_jb_sparse_attn_tc",
     "llark_quick_gelu", "llark_add3", "llark_jb_pool", "llark_jb_pool_batched", "llark_colsum",
-    "llark_init", "llark_jb_label_cond", "llark_v32_split_tf32", "llark_v32_embed_splice_fwd", "llark_v32_rmsnorm_fwd", "llark_v32_rope",
+    "llark_init", "llark_attn_bwd_rope", "llark_jb_label_cond", "llark_v32_split_tf32", "llark_v32_embed_splice_fwd", "llark_v32_rmsnorm_fwd", "llark_v32_rope",
     "llark_v32_swiglu_fwd", "llark_v32_attn_fwd", "llark_v32_ce_fwd",
 ]
 
@@ -111,6 +111,7 @@ def lib():
             "llark_jb_pool_batched": ([P, P, I, LL, I, I, I, P], I),
             "llark_colsum": ([P, P, LL, I, I, P], I),
             "llark_init": ([], I),
+            "llark_attn_bwd_rope": ([P, P, P, P, P, P, I, I, I, I, F, P, P, P, P], I),
             "llark_jb_label_cond": ([P, P, P, P, P, P, I, I, P], I),
             "llark_v32_split_tf32": ([P, P, P, LL, P], I),
             "llark_v32_embed_splice_fwd": ([P, P, P, P, P, P, P, I, I, I, LL, P], I),

@@ -18,13 +18,14 @@ extern thread_local int g_last_cuda_error;
 int attn_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S, int n_heads,
                        float scale, cudaStream_t st);  // attention_tc.cu
 int attn_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
-                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, cudaStream_t st);
+                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, const void* rope_cos,
+                       const void* rope_sin, cudaStream_t st);  // rope_cos != null: inverse RoPE of dq | dk fused
 // ALiBi instantiation (attention_tc_alibi.cu) for the MPT variant: same kernels + slope_h * key on the scores
 int attn_alibi_fwd_tc_launch(const void* qkv, const unsigned char* key_mask, void* out, float* lse, int B, int S,
                              int n_heads, float scale, const float* slopes, cudaStream_t st);
 int attn_alibi_bwd_tc_launch(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
-                             const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, const float* slopes,
-                             cudaStream_t st);
+                             const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, const void* rope_cos,
+                             const void* rope_sin, const float* slopes, cudaStream_t st);
 // LLARK_ATTN_TC bit 0: tcgen05 forward, bit 1: tcgen05 backward. Default 3 (both, validated on B200: same test
 // tolerances as the mma.sync kernels, forward 202 -> 89 us and backward 717 -> 481 us at B 16, S 512, 32 heads);
 // 0 selects the mma.sync kernels of this file (also used for S > 4096).
@@ -666,10 +667,15 @@ extern "C" long long llark_attn_bwd_workspace(int B, int S, int n_heads) {
     return (long long)B * S * n_heads * (long long)sizeof(float);
 }
 
-extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
-                              const float* lse, void* dqkv, int B, int S, int n_heads, int head_dim, float scale,
-                              void* workspace, cudaStream_t st) {
+// Backward of the causal attention into dqkv = (dq | dk | dv). rope_cos / rope_sin (bf16 [S, 128], null = none): the
+// inverse rotary embedding is applied to the dq and dk heads on the way out -- inside the tcgen05 kernels' epilogues
+// (attention_tc.cu: store_acc_64_irope), or by llark_rope(inverse) after the mma.sync kernels (S > 4096) -- so that dqkv
+// is the gradient of the PRE-RoPE projection output, bit-identical to llark_attn_bwd followed by llark_rope(inverse=1).
+static int attn_bwd_impl(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                         const float* lse, void* dqkv, int B, int S, int n_heads, int head_dim, float scale,
+                         const void* rope_cos, const void* rope_sin, void* workspace, cudaStream_t st) {
     if (head_dim != HD || B <= 0 || S <= 0 || n_heads <= 0 || !workspace) return LLARK_EINVAL;
+    if ((rope_cos == nullptr) != (rope_sin == nullptr)) return LLARK_EINVAL;
     float* Dsum = (float*)workspace;
     const long long warps = (long long)B * S * n_heads;
     attn_bwd_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out,
@@ -678,7 +684,8 @@ extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, co
     int rc = check_launch2();
     if (rc) return rc;
     if (attn_tc_mode() & 2) {
-        const int rc_tc = attn_bwd_tc_launch(qkv, key_mask, dout, lse, Dsum, dqkv, B, S, n_heads, scale, st);
+        const int rc_tc = attn_bwd_tc_launch(qkv, key_mask, dout, lse, Dsum, dqkv, B, S, n_heads, scale, rope_cos,
+                                             rope_sin, st);
         if (rc_tc != LLARK_EINVAL) return rc_tc;
     }
     rc = set_smem((const void*)attn_bwd_dkdv_kernel, DKDV_SMEM);
@@ -692,7 +699,23 @@ extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, co
     if (rc) return rc;
     attn_bwd_dq_kernel<<<grid, 128, DQ_SMEM, st>>>((const __nv_bfloat16*)qkv, key_mask, (const __nv_bfloat16*)dout, lse,
                                                    Dsum, (__nv_bfloat16*)dqkv, S, n_heads, scale, scale * LOG2E);
-    return check_launch2();
+    rc = check_launch2();
+    if (rc || !rope_cos) return rc;
+    return llark_rope(dqkv, rope_cos, rope_sin, (long long)B * S, S, n_heads, HD, 3LL * n_heads * HD, 1, st);
+}
+
+extern "C" int llark_attn_bwd(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                              const float* lse, void* dqkv, int B, int S, int n_heads, int head_dim, float scale,
+                              void* workspace, cudaStream_t st) {
+    return attn_bwd_impl(qkv, key_mask, out, dout, lse, dqkv, B, S, n_heads, head_dim, scale, nullptr, nullptr, workspace,
+                         st);
+}
+extern "C" int llark_attn_bwd_rope(const void* qkv, const unsigned char* key_mask, const void* out, const void* dout,
+                                   const float* lse, void* dqkv, int B, int S, int n_heads, int head_dim, float scale,
+                                   const void* rope_cos, const void* rope_sin, void* workspace, cudaStream_t st) {
+    if (!rope_cos || !rope_sin) return LLARK_EINVAL;
+    return attn_bwd_impl(qkv, key_mask, out, dout, lse, dqkv, B, S, n_heads, head_dim, scale, rope_cos, rope_sin, workspace,
+                         st);
 }
 
 // ---------------------------------------------------------------------------------------------- ALiBi (MPT variant)
@@ -716,5 +739,6 @@ extern "C" int llark_attn_alibi_bwd(const void* qkv, const unsigned char* key_ma
                                                                                 n_heads);
     int rc = check_launch2();
     if (rc) return rc;
-    return attn_alibi_bwd_tc_launch(qkv, key_mask, dout, lse, Dsum, dqkv, B, S, n_heads, scale, slopes, st);
+    return attn_alibi_bwd_tc_launch(qkv, key_mask, dout, lse, Dsum, dqkv, B, S, n_heads, scale, nullptr, nullptr, slopes,
+                                    st);
 }

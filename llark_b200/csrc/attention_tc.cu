@@ -479,6 +479,51 @@ __device__ __forceinline__ void store_acc_64(uint32_t taddr, __nv_bfloat16* dst,
     }
 }
 
+// The same 64 output columns with the INVERSE rotary embedding applied on the way out (the gradient of
+// apply_rotary_pos_emb w.r.t. its input, what llark_rope(inverse=1) does to the dq | dk columns after an unfused
+// backward). The rotation partner of column d is column d +- 64 of the same row, i.e. the OTHER half of this thread's
+// TMEM lane, so every thread reads both halves and writes its own:
+//   half 0:  o[d]      = bf16(x[d] * cos[d])           + bf16( x[d + 64] * sin[d + 64])
+//   half 1:  o[d + 64] = bf16(x[d + 64] * cos[d + 64]) + bf16(-x[d] * sin[d])        with x = bf16(acc * mul),
+// the rounding points of rope_kernel (llama_ops.cu) on the bf16 values the unfused path would have stored: bit-identical.
+// cs / sn: this row's 128 cos / sin values (bf16, position = row % S).
+__device__ __forceinline__ void store_acc_64_irope(uint32_t taddr_row, int g, __nv_bfloat16* dst, float mul, bool ok,
+                                                   const __nv_bfloat16* cs, const __nv_bfloat16* sn) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        uint32_t own[32], oth[32];
+        tmem_ld_32x32b_x32(taddr_row + g * 64 + c * 32, own);
+        tmem_ld_32x32b_x32(taddr_row + (1 - g) * 64 + c * 32, oth);
+        tmem_ld_wait();
+        if (ok) {
+            const int d0 = c * 32;  // index inside the half
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // cos of the OWN column, sin of the PARTNER's column (see the formulas above)
+                const uint4 cw = *reinterpret_cast<const uint4*>(cs + g * 64 + d0 + u * 8);
+                const uint4 sw = *reinterpret_cast<const uint4*>(sn + (1 - g) * 64 + d0 + u * 8);
+                const uint32_t cwv[4] = {cw.x, cw.y, cw.z, cw.w}, swv[4] = {sw.x, sw.y, sw.z, sw.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const float2 cc = unpack_bf16x2(cwv[e2]), ss = unpack_bf16x2(swv[e2]);
+                    float r[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int e = u * 8 + e2 * 2 + q;
+                        const float xo = bf16_round(__uint_as_float(own[e]) * mul);
+                        const float xp = bf16_round(__uint_as_float(oth[e]) * mul);
+                        const float cv = q ? cc.y : cc.x, sv = q ? ss.y : ss.x;
+                        r[q] = bf16_round(xo * cv) + bf16_round((g ? -xp : xp) * sv);
+                    }
+                    ow[e2] = pack_bf16x2(r[0], r[1]);
+                }
+                *reinterpret_cast<uint4*>(dst + d0 + u * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- dQ
 constexpr int DQ_OFF_DO = Q_BYTES;
 constexpr int DQ_OFF_RING = 2 * Q_BYTES;
@@ -491,7 +536,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                       const unsigned char* __restrict__ mask, const float* __restrict__ lse,
                       const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
-                      float scale_log2 LLARK_ATC_SLOPES_PARAM) {
+                      float scale_log2, const __nv_bfloat16* __restrict__ rope_cos,
+                      const __nv_bfloat16* __restrict__ rope_sin LLARK_ATC_SLOPES_PARAM) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -661,7 +707,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         mbar_wait(&dq_done[(n_kv - 1) & 1], (uint32_t)((n_kv - 1) >> 1) & 1);  // MMAs retire in order
         tc_fence_after();
         __nv_bfloat16* dqp = dqkv + ((long long)b * S + qi) * (3LL * NH * HD) + (long long)h * HD + g * 64;
-        store_acc_64(lane_base + 256 + g * 64, dqp, scale, row_ok);
+        if (rope_cos)  // inverse RoPE of dq fused into the store (position = query index)
+            store_acc_64_irope(lane_base + 256, g, dqp, scale, row_ok, rope_cos + (long long)(row_ok ? qi : 0) * HD,
+                               rope_sin + (long long)(row_ok ? qi : 0) * HD);
+        else
+            store_acc_64(lane_base + 256 + g * 64, dqp, scale, row_ok);
         tc_fence_before();
     }
 
@@ -687,7 +737,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const unsigned char* __restrict__ mask, const float* __restrict__ lse,
                         const float* __restrict__ Dsum, __nv_bfloat16* __restrict__ dqkv, int S, int NH, float scale,
-                        float scale_log2 LLARK_ATC_SLOPES_PARAM) {
+                        float scale_log2, const __nv_bfloat16* __restrict__ rope_cos,
+                        const __nv_bfloat16* __restrict__ rope_sin LLARK_ATC_SLOPES_PARAM) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -871,7 +922,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                              g * 64;
         __nv_bfloat16* dvp = dkp + (long long)NH * HD;
         store_acc_64(lane_base + 256 + g * 64, dvp, 1.f, key < S);
-        store_acc_64(lane_base + 384 + g * 64, dkp, scale, key < S);
+        if (rope_cos)  // inverse RoPE of dk fused into the store (position = key index)
+            store_acc_64_irope(lane_base + 384, g, dkp, scale, key < S, rope_cos + (long long)(key < S ? key : 0) * HD,
+                               rope_sin + (long long)(key < S ? key : 0) * HD);
+        else
+            store_acc_64(lane_base + 384 + g * 64, dkp, scale, key < S);
         tc_fence_before();
     }
 
@@ -919,8 +974,8 @@ int LLARK_ATC_FWD_LAUNCH(const void* qkv, const unsigned char* key_mask, void* o
 // Backward (dq|dk|dv into dqkv) on tcgen05; Dsum must already hold rowsum(dO o O). LLARK_EINVAL = shape outside the
 // envelope (caller falls back to the mma.sync kernels).
 int LLARK_ATC_BWD_LAUNCH(const void* qkv, const unsigned char* key_mask, const void* dout, const float* lse,
-                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale LLARK_ATC_SLOPES_PARAM,
-                       cudaStream_t st) {
+                       const float* Dsum, void* dqkv, int B, int S, int n_heads, float scale, const void* rope_cos,
+                       const void* rope_sin LLARK_ATC_SLOPES_PARAM, cudaStream_t st) {
     using namespace LLARK_ATC_NS;
     if ((long long)B * S > 0x7fffffffLL || S > MAX_S) return LLARK_EINVAL;
     CUtensorMap tq, td;
@@ -943,9 +998,13 @@ int LLARK_ATC_BWD_LAUNCH(const void* qkv, const unsigned char* key_mask, const v
     }
     dim3 grid((S + BQ - 1) / BQ, n_heads, B);
     attn_bwd_dkdv_tc_kernel<<<grid, kBwdThreads, KV_SMEM_BYTES, st>>>(tq, td, key_mask, lse, Dsum, (__nv_bfloat16*)dqkv,
-                                                                      S, n_heads, scale, scale * LOG2E LLARK_ATC_SLOPES_ARG);
+                                                                      S, n_heads, scale, scale * LOG2E,
+                                                                      (const __nv_bfloat16*)rope_cos,
+                                                                      (const __nv_bfloat16*)rope_sin LLARK_ATC_SLOPES_ARG);
     attn_bwd_dq_tc_kernel<<<grid, kBwdThreads, DQ_SMEM_BYTES, st>>>(tq, td, key_mask, lse, Dsum, (__nv_bfloat16*)dqkv, S,
-                                                                    n_heads, scale, scale * LOG2E LLARK_ATC_SLOPES_ARG);
+                                                                    n_heads, scale, scale * LOG2E,
+                                                                    (const __nv_bfloat16*)rope_cos,
+                                                                    (const __nv_bfloat16*)rope_sin LLARK_ATC_SLOPES_ARG);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         g_last_cuda_error = (int)e;

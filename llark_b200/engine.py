@@ -537,10 +537,15 @@ class LlamaEngine:
             # attention
             dattn = ops.gemm(dx_mid, Wo, b_mn=True)
             n0 += 3 + wgrad(pfx + "self_attn.o_proj.weight", dx_mid, attn, (H, H))
-            dqkv = ops.attn_bwd(qkv, sv["mask"], attn, dattn, lse, B, S, NH, D, workspace=ws_attn)
-            ops.rope_(dqkv, cos, sin, S, NH, D, inverse=True)
+            if self.fuse_epilogues and D == 128:
+                # inverse RoPE of dq | dk in the attention backward's epilogues (bit-identical to attn_bwd -> llark_rope)
+                dqkv = ops.attn_bwd(qkv, sv["mask"], attn, dattn, lse, B, S, NH, D, workspace=ws_attn, rope=(cos, sin))
+            else:
+                dqkv = ops.attn_bwd(qkv, sv["mask"], attn, dattn, lse, B, S, NH, D, workspace=ws_attn)
+                ops.rope_(dqkv, cos, sin, S, NH, D, inverse=True)
+                n0 += 1
             dxn1 = ops.gemm(dqkv, Wqkv, b_mn=True)
-            n0 += 5 + wgrad(pfx + "self_attn.q_proj.weight", dqkv, xn1, (3 * H, H), span=3)
+            n0 += 4 + wgrad(pfx + "self_attn.q_proj.weight", dqkv, xn1, (3 * H, H), span=3)
             ops.rmsnorm_bwd(x, flat.pview(pfx + "input_layernorm.weight"), dxn1, rstd1, dx_mid, dx,
                             flat.gview(pfx + "input_layernorm.weight"), acc, ws_norm)
             n0 += 2

@@ -202,11 +202,19 @@ def attn_decode(q, k_cache, v_cache, lens, n_heads, head_dim, out=None):
     return out
 
 
-def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None):
+def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None, rope=None):
+    """dqkv = (dq | dk | dv). rope=(cos, sin) (bf16 [>= S, head_dim]): the inverse rotary embedding of the dq | dk heads is
+    fused into the backward kernels (llark_attn_bwd_rope), bit-identical to attn_bwd followed by rope_(inverse=True)."""
     dqkv = dqkv if dqkv is not None else torch.empty_like(qkv)
     need = lib().llark_attn_bwd_workspace(B, S, n_heads)
     if workspace is None:
         workspace = torch.empty(need, device=qkv.device, dtype=torch.uint8)
+    if rope is not None:
+        cos_t, sin_t = rope
+        check(lib().llark_attn_bwd_rope(_p(qkv), _p(key_mask), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, n_heads,
+                                        head_dim, 1.0 / math.sqrt(head_dim), _p(_req(cos_t, BF16)), _p(_req(sin_t, BF16)),
+                                        _p(workspace), _stream()), "attn_bwd_rope")
+        return dqkv
     check(lib().llark_attn_bwd(_p(qkv), _p(key_mask), _p(out), _p(dout), _p(lse), _p(dqkv), B, S, n_heads, head_dim,
                                1.0 / math.sqrt(head_dim), _p(workspace), _stream()), "attn_bwd")
     return dqkv

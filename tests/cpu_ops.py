@@ -231,7 +231,10 @@ def rmsnorm_bwd(x, w, dy, rstd, dres, dx, dw, accumulate_dw, workspace):
     return dx
 
 
-def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None):
+def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, workspace=None, rope=None):
+    if rope is not None:  # fused form: inverse RoPE of dq | dk applied on the way out
+        g = attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim)
+        return rope_(g, rope[0], rope[1], S, n_heads, head_dim, inverse=True)
     x = qkv.float().clone().requires_grad_(True)
     with torch.enable_grad():
         q, k, v = x.view(B, S, 3, n_heads, head_dim).permute(2, 0, 3, 1, 4)

@@ -343,6 +343,30 @@ def test_attention_fwd_bwd(B, S, NH, pad):
         assert _rel(got[:, :, i], g[:, :, i]) < 1.5e-2, name
 
 
+@pytest.mark.parametrize("B,S,NH,pad", [(2, 512, 4, True), (1, 200, 2, False), (1, 4160, 1, True)])
+def test_attention_bwd_with_fused_inverse_rope_is_bit_identical(B, S, NH, pad):
+    """llark_attn_bwd_rope == llark_attn_bwd followed by llark_rope(inverse=1), bit for bit: on the tcgen05 kernels (rotation
+    in the dq / dk epilogues) and beyond their envelope (S = 4160: mma.sync kernels + the rope kernel inside the call)."""
+    ops = _ops()
+    D, H = 128, NH * 128
+    g = torch.Generator(device="cuda").manual_seed(S + NH)
+    qkv = (torch.randn(B * S, 3 * H, device="cuda", generator=g) * 0.7).to(BF16)
+    dout = torch.randn(B * S, H, device="cuda", generator=g).to(BF16)
+    mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+    if pad:
+        mask[-1, S - 37:] = False
+    mask_u8 = mask.view(torch.uint8)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device="cuda").float() / D))
+    emb = torch.cat((torch.arange(S, device="cuda").float()[:, None] * inv[None],) * 2, dim=-1)
+    cos, sin = emb.cos().to(BF16).contiguous(), emb.sin().to(BF16).contiguous()
+    out, lse = ops.attn_fwd(qkv, mask_u8, B, S, NH, D)
+    want = ops.attn_bwd(qkv, mask_u8, out, dout, lse, B, S, NH, D)
+    ops.rope_(want, cos, sin, S, NH, D, inverse=True)
+    got = ops.attn_bwd(qkv, mask_u8, out, dout, lse, B, S, NH, D, rope=(cos, sin))
+    valid = mask.view(-1)
+    assert torch.equal(got[valid], want[valid])
+
+
 @pytest.mark.parametrize("B,S,NH,pad", [(1, 2048, 2, True),     # the reference's --model_max_length (train_llark.sh)
                                         (1, 4096, 1, False),    # upper edge of the tcgen05 kernels' envelope
                                         (1, 4160, 1, True)])    # beyond it: llark_attn_* must fall back to mma.sync
