@@ -62,6 +62,8 @@ struct GemmParams {
     // position = row % epi_i0, epi_a / epi_b = cos / sin bf16 [S,128]), 3 SwiGLU backward (epi_a = gu bf16 [M, epi_ld]:
     // gate | up halves N apart; C receives dgate at column c and dup at column N + c)
     int staged;      // 1 = staged (coalesced) epilogue, 0 = direct row-per-thread stores (see epilogue_dispatch)
+    int group_m;     // m-blocks per rasterisation group (tile_coord): sized on the host so a group's A panel stays in L2
+    int prefetch;    // 1 = the epilogue warps L2-prefetch the NEXT tile's residual / gate|up rows one tile ahead
     int epi;
     const void* epi_a;
     const void* epi_b;
@@ -100,8 +102,7 @@ struct TileCoord {
 };
 // Grouped rasterisation: 16 m-blocks share a sweep over n so that the ~148 tiles in flight reuse
 // A/B panels out of L2.
-__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks) {
-    constexpr int GROUP_M = 16;
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks, int GROUP_M = 16) {
     const int tiles_per_group = GROUP_M * num_n_blocks;
     const int group = tile / tiles_per_group;
     const int first_m = group * GROUP_M;
@@ -468,6 +469,33 @@ __device__ __forceinline__ void epi_staged_bf16(const GemmParams& p, long long r
     }
 }
 
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+// L2 prefetch of what the epilogue of an UPCOMING tile will read besides the accumulator: this thread's row of the
+// residual R (or, for the SwiGLU backward, of gate | up). Measured motivation: with a residual the epilogue is a chain of
+// (global load -> add -> store) per 32-column chunk, each warp has one chunk of loads in flight, and at ~2.4 us of loaded
+// DRAM latency eight chunks cost ~18 us per tile -- more than the tile's MMAs for K <= 4800 (prior c_proj: 28 % tensor-pipe
+// active, profiles/r2f_prof_prior_gemm_hbm.md). One cp.async.bulk.prefetch.L2 per row per tile, issued a whole tile ahead,
+// costs no registers and turns those loads into L2 hits.
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, long long row, int ncol0) {
+    if (row >= p.M || ncol0 >= p.N) return;
+    const int ncols = min(BLOCK_N, p.N - ncol0);
+    if constexpr (EPI == 3) {
+        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.epi_a) + row * p.epi_ld + ncol0;
+        const uint32_t bytes = (uint32_t)(ncols * 2) & ~15u;
+        if (bytes) {
+            prefetch_l2_bulk(g, bytes);
+            prefetch_l2_bulk(g + p.N, bytes);
+        }
+    } else if (p.R) {
+        const int eb = p.c_fp32 ? 4 : 2;
+        const uint32_t bytes = (uint32_t)(ncols * eb) & ~15u;
+        if (bytes) prefetch_l2_bulk(reinterpret_cast<const char*>(p.R) + (row * p.ldr + ncol0) * eb, bytes);
+    }
+}
+
 // Epilogue of one 128 x 256 accumulator tile for the warp owning TMEM lanes [32 ew, 32 ew + 32): rows row0 .. row0 + 31.
 // The RoPE columns of a fused-QKV projection keep the row-per-thread path (rotation partners are 64 columns apart).
 // p.staged (chosen on the host, llark_gemm_ex) selects the staged path where the epilogue is the longer leg: fp32 output
@@ -537,7 +565,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
             const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -622,7 +650,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int ew = warp - 4;  // TMEM lane quadrant
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
@@ -780,7 +808,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = next_tile(false); tile >= 0; tile = next_tile(false)) {
-            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
             const int m0 = tc.m_blk * 256 + (int)rank * 128;
             const int n0 = tc.n_blk * BLOCK_N + (int)rank * 128;
             const int m_chunk = m0 / mn_per_box, n_chunk = n0 / mn_per_box;  // once per tile, not per stage
@@ -889,8 +917,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int ew = warp - 4;
         int it = 0;
         const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
-        for (int tile = next_tile(true); tile >= 0; tile = next_tile(true), ++it) {
-            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks);
+        // the tile index is read ONE tile ahead of the tile being written out, so that its residual rows can be requested
+        // from DRAM a whole epilogue early (epilogue_prefetch); the number of scheduler reads is unchanged
+        int tile = next_tile(true);
+        int tile_next = tile >= 0 ? next_tile(true) : -1;
+        if (p.prefetch && tile >= 0) {
+            const TileCoord t0 = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
+            epilogue_prefetch<EPI>(p, (long long)t0.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane, t0.n_blk * BLOCK_N);
+        }
+        for (; tile >= 0; ++it) {
+            const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
+            if (p.prefetch && tile_next >= 0) {
+                const TileCoord tn = tile_coord(tile_next, p.num_m_blocks, p.num_n_blocks, p.group_m);
+                epilogue_prefetch<EPI>(p, (long long)tn.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane,
+                                       tn.n_blk * BLOCK_N);
+            }
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
@@ -901,6 +942,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_empty0 + (uint32_t)as * 8u);
+            tile = tile_next;
+            if (tile >= 0) tile_next = next_tile(true);
         }
     }
 
@@ -1262,6 +1305,29 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
             mode = (e && e[0] == 's') ? 1 : ((e && e[0] == 'd') ? 2 : 0);
         }
         p.staged = mode == 1 ? 1 : (mode == 2 ? 0 : ((c_fp32 || p.epi == LLARK_EPI_SWIGLU_BWD) ? 1 : 0));
+    }
+    {
+        // Rasterisation group: tiles sweep n inside groups of `group_m` m-blocks, so a group's A panel
+        // (group_m x tile_m rows x K) is re-used across the sweep. Sized so that panel stays L2-resident (LLARK_GEMM_L2_MB,
+        // default 0 = the fixed 16 of round 1): ncu shows 3.5-4.4x the algorithmic DRAM bytes on the K >= 11008 shapes with
+        // the fixed group (profiles/gemm_traffic.json).
+        static int l2_mb = -1;
+        if (l2_mb < 0) {
+            const char* e = getenv("LLARK_GEMM_L2_MB");
+            l2_mb = e ? atoi(e) : 0;
+        }
+        p.group_m = 16;
+        if (l2_mb > 0) {
+            const double per_mblock = (double)(two_cta ? 256 : BLOCK_M) * K * eb;
+            int g = (int)((double)l2_mb * 1e6 / per_mblock);
+            p.group_m = g < 2 ? 2 : (g > 32 ? 32 : g);
+        }
+        static int pf = -1;
+        if (pf < 0) {
+            const char* e = getenv("LLARK_GEMM_PREFETCH");
+            pf = e ? atoi(e) : 1;
+        }
+        p.prefetch = (pf && two_cta && (R != nullptr || p.epi == LLARK_EPI_SWIGLU_BWD)) ? 1 : 0;
     }
     p.epi_a = ep ? ep->a : nullptr;
     p.epi_b = ep ? ep->b : nullptr;
