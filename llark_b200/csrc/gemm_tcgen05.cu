@@ -63,7 +63,6 @@ struct GemmParams {
     // gate | up halves N apart; C receives dgate at column c and dup at column N + c)
     int staged;      // 1 = staged (coalesced) epilogue, 0 = direct row-per-thread stores (see epilogue_dispatch)
     int group_m;     // m-blocks per rasterisation group (tile_coord): sized on the host so a group's A panel stays in L2
-    int prefetch;    // 1 = the epilogue warps L2-prefetch the NEXT tile's residual / gate|up rows one tile ahead
     int epi;
     const void* epi_a;
     const void* epi_b;
@@ -466,33 +465,6 @@ __device__ __forceinline__ void epi_staged_bf16(const GemmParams& p, long long r
                 if (EPI == 3) uc[i] = un[i];
             }
         }
-    }
-}
-
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-// L2 prefetch of what the epilogue of an UPCOMING tile will read besides the accumulator: this thread's row of the
-// residual R (or, for the SwiGLU backward, of gate | up). Measured motivation: with a residual the epilogue is a chain of
-// (global load -> add -> store) per 32-column chunk, each warp has one chunk of loads in flight, and at ~2.4 us of loaded
-// DRAM latency eight chunks cost ~18 us per tile -- more than the tile's MMAs for K <= 4800 (prior c_proj: 28 % tensor-pipe
-// active, profiles/r2f_prof_prior_gemm_hbm.md). One cp.async.bulk.prefetch.L2 per row per tile, issued a whole tile ahead,
-// costs no registers and turns those loads into L2 hits.
-template <int EPI>
-__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, long long row, int ncol0) {
-    if (row >= p.M || ncol0 >= p.N) return;
-    const int ncols = min(BLOCK_N, p.N - ncol0);
-    if constexpr (EPI == 3) {
-        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.epi_a) + row * p.epi_ld + ncol0;
-        const uint32_t bytes = (uint32_t)(ncols * 2) & ~15u;
-        if (bytes) {
-            prefetch_l2_bulk(g, bytes);
-            prefetch_l2_bulk(g + p.N, bytes);
-        }
-    } else if (p.R) {
-        const int eb = p.c_fp32 ? 4 : 2;
-        const uint32_t bytes = (uint32_t)(ncols * eb) & ~15u;
-        if (bytes) prefetch_l2_bulk(reinterpret_cast<const char*>(p.R) + (row * p.ldr + ncol0) * eb, bytes);
     }
 }
 
@@ -917,21 +889,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
         const int ew = warp - 4;
         int it = 0;
         const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
-        // the tile index is read ONE tile ahead of the tile being written out, so that its residual rows can be requested
-        // from DRAM a whole epilogue early (epilogue_prefetch); the number of scheduler reads is unchanged
-        int tile = next_tile(true);
-        int tile_next = tile >= 0 ? next_tile(true) : -1;
-        if (p.prefetch && tile >= 0) {
-            const TileCoord t0 = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
-            epilogue_prefetch<EPI>(p, (long long)t0.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane, t0.n_blk * BLOCK_N);
-        }
-        for (; tile >= 0; ++it) {
+        for (int tile = next_tile(true); tile >= 0; tile = next_tile(true), ++it) {
             const TileCoord tc = tile_coord(tile, p.num_m_blocks, p.num_n_blocks, p.group_m);
-            if (p.prefetch && tile_next >= 0) {
-                const TileCoord tn = tile_coord(tile_next, p.num_m_blocks, p.num_n_blocks, p.group_m);
-                epilogue_prefetch<EPI>(p, (long long)tn.m_blk * 256 + (long long)rank * 128 + ew * 32 + lane,
-                                       tn.n_blk * BLOCK_N);
-            }
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full[as], aphase);
@@ -942,8 +901,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_empty0 + (uint32_t)as * 8u);
-            tile = tile_next;
-            if (tile >= 0) tile_next = next_tile(true);
         }
     }
 
@@ -1308,9 +1265,11 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
     }
     {
         // Rasterisation group: tiles sweep n inside groups of `group_m` m-blocks, so a group's A panel
-        // (group_m x tile_m rows x K) is re-used across the sweep. Sized so that panel stays L2-resident (LLARK_GEMM_L2_MB,
-        // default 0 = the fixed 16 of round 1): ncu shows 3.5-4.4x the algorithmic DRAM bytes on the K >= 11008 shapes with
-        // the fixed group (profiles/gemm_traffic.json).
+        // (group_m x tile_m rows x K) is re-used across the sweep. ncu shows 3.5-4.4x the algorithmic DRAM bytes on the
+        // K >= 11008 shapes with the fixed group of 16 (profiles/gemm_traffic.json); LLARK_GEMM_L2_MB=<MB> sizes the group so
+        // that panel fits that many MB of L2 instead. Measured (profiles/r2g_negative_results.md): 32 and 48 MB leave every
+        // shape's in-step rate within +-1 % -- DRAM is at ~35 % of its bandwidth on these kernels either way -- so the default
+        // stays the fixed 16 (0).
         static int l2_mb = -1;
         if (l2_mb < 0) {
             const char* e = getenv("LLARK_GEMM_L2_MB");
@@ -1322,25 +1281,6 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
             int g = (int)((double)l2_mb * 1e6 / per_mblock);
             p.group_m = g < 2 ? 2 : (g > 32 ? 32 : g);
         }
-        static int pf = -1;
-        if (pf < 0) {
-            const char* e = getenv("LLARK_GEMM_PREFETCH");
-            pf = e ? atoi(e) : 1;
-        }
-        p.prefetch = (pf && two_cta && (R != nullptr || p.epi == LLARK_EPI_SWIGLU_BWD)) ? 1 : 0;
-    }
-    p.epi_a = ep ? ep->a : nullptr;
-    p.epi_b = ep ? ep->b : nullptr;
-    p.epi_ld = ep ? ep->ld : 0;
-    p.epi_i0 = ep ? ep->i0 : 0;
-    p.epi_i1 = ep ? ep->i1 : 0;
-    {
-        static int dbg = -1;
-        if (dbg < 0) {
-            const char* e = getenv("LLARK_GEMM_DEBUG");
-            dbg = e ? atoi(e) : 0;
-        }
-        p.debug = dbg;
     }
 
     const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);

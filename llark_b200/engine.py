@@ -174,15 +174,6 @@ class LlamaEngine:
         # not fit comfortably in free HBM (a 7B step at S=512, B=16 keeps 35 GB and does not need it); "1" / "0" force it.
         self.recompute = os.environ.get("LLARK_RECOMPUTE", "auto")
         self.recomputed_last_step = False
-        # Weight-gradient GEMMs on a side stream (LLARK_WGRAD_STREAM=0: everything on one stream). Every dgrad / wgrad pair
-        # of the backward is independent and nothing consumes a wgrad before the optimizer, so the wgrads are enqueued on
-        # their own stream behind an event: when a persistent GEMM runs out of tiles (its last, partial wave: 256x256 tiles
-        # on 74 CTA pairs leave e.g. `wgrad M4096 N4096` at 3.46 waves) the SMs it releases are taken at once by the next
-        # kernel of the OTHER stream instead of idling until the whole grid has drained. Results are bit-identical (same
-        # kernels, same operands); tensors a side-stream kernel reads are pinned with record_stream.
-        self.wgrad_stream_enabled = os.environ.get("LLARK_WGRAD_STREAM", "1") != "0"
-        self._wgrad_stream = None
-        self.slice_ready_events = []  # events (side stream) a just-announced gradient slice also depends on
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named(self):
@@ -483,28 +474,12 @@ class LlamaEngine:
         ws_norm = self._workspace("norm", ops.lib().llark_rmsnorm_bwd_workspace(M, H), dev)
         ws_attn = self._workspace("attn", ops.lib().llark_attn_bwd_workspace(B, S, NH), dev)
 
-        side = None
-        if self.wgrad_stream_enabled and dev.type == "cuda" and ops.GEMM_PROFILE is None:
-            # (per-launch event timing -- bench.py's roofline pass -- needs launches that do not overlap: one stream then)
-            if self._wgrad_stream is None or self._wgrad_stream.device != dev:
-                self._wgrad_stream = torch.cuda.Stream(device=dev)
-            side = self._wgrad_stream
-
-        def wgrad(name, dy, xin, shape, span=1, **kw):
+        def wgrad(name, dy, xin, shape, span=1):
             """dW[N,K] (+)= dy[M,N]^T @ xin[M,K] written straight into the flat gradient bucket."""
             g = flat.gview(name, shape, span=span)
             if g is None:
                 return 0
-            if side is None:
-                ops.gemm(dy, xin, a_mn=True, b_mn=True, out=g, residual=g if acc else None, **kw)
-                return 1
-            ready = torch.cuda.Event()
-            ready.record()                      # dy / xin (and everything before) are complete on the main stream
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                ops.gemm(dy, xin, a_mn=True, b_mn=True, out=g, residual=g if acc else None, **kw)
-            dy.record_stream(side)              # the caching allocator must not hand these out again before the
-            xin.record_stream(side)             # side-stream kernel has read them
+            ops.gemm(dy, xin, a_mn=True, b_mn=True, out=g, residual=g if acc else None)
             return 1
 
         # loss -> dlogits -> d(final hidden)
@@ -545,25 +520,23 @@ class LlamaEngine:
             if self.fuse_epilogues:
                 # d(act)[M,I] = dx[M,H] @ Wd[H,I] never reaches HBM: the dgrad's epilogue applies the SwiGLU backward
                 # and writes dgu = (dgate | dup) directly (bit-identical to gemm -> llark_swiglu_bwd)
-                # (each wgrad is issued BEFORE its sibling dgrad: its operands are ready at this point, so on the side
-                # stream it can start alongside the dgrad instead of after it)
-                n0 += 1 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
                 dgu = torch.empty_like(gu)
                 ops.gemm(dx, Wd, b_mn=True, out=dgu, N=I, swiglu_bwd=gu)
+                n0 += 1 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
             else:
-                n0 += 2 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
                 dact = ops.gemm(dx, Wd, b_mn=True)  # [M,I] = dx[M,H] @ Wd[H,I]
+                n0 += 2 + wgrad(pfx + "mlp.down_proj.weight", dx, act, (H, I))
                 dgu = ops.swiglu_bwd(gu, dact)
                 del dact
-            n0 += 1 + wgrad(pfx + "mlp.gate_proj.weight", dgu, xn2, (2 * I, H), span=2)
             dxn2 = ops.gemm(dgu, Wgu, b_mn=True)  # [M,H] = dgu[M,2I] @ Wgu[2I,H]
+            n0 += 1 + wgrad(pfx + "mlp.gate_proj.weight", dgu, xn2, (2 * I, H), span=2)
             del dgu
             dx_mid = torch.empty((M, H), device=dev, dtype=BF16)
             ops.rmsnorm_bwd(x_mid, flat.pview(pfx + "post_attention_layernorm.weight"), dxn2, rstd2, dx, dx_mid,
                             flat.gview(pfx + "post_attention_layernorm.weight"), acc, ws_norm)
             # attention
-            n0 += 3 + wgrad(pfx + "self_attn.o_proj.weight", dx_mid, attn, (H, H))
             dattn = ops.gemm(dx_mid, Wo, b_mn=True)
+            n0 += 3 + wgrad(pfx + "self_attn.o_proj.weight", dx_mid, attn, (H, H))
             if self.fuse_epilogues and D == 128:
                 # inverse RoPE of dq | dk in the attention backward's epilogues (bit-identical to attn_bwd -> llark_rope)
                 dqkv = ops.attn_bwd(qkv, sv["mask"], attn, dattn, lse, B, S, NH, D, workspace=ws_attn, rope=(cos, sin))
@@ -571,14 +544,10 @@ class LlamaEngine:
                 dqkv = ops.attn_bwd(qkv, sv["mask"], attn, dattn, lse, B, S, NH, D, workspace=ws_attn)
                 ops.rope_(dqkv, cos, sin, S, NH, D, inverse=True)
                 n0 += 1
-            n0 += 4 + wgrad(pfx + "self_attn.q_proj.weight", dqkv, xn1, (3 * H, H), span=3)
             dxn1 = ops.gemm(dqkv, Wqkv, b_mn=True)
-            # (with the side stream the down-projection wgrad of THIS layer may still be reading dx: write the next
-            # layer's dx into a fresh buffer instead of in place)
-            dx_next = torch.empty_like(dx) if side is not None else dx
-            ops.rmsnorm_bwd(x, flat.pview(pfx + "input_layernorm.weight"), dxn1, rstd1, dx_mid, dx_next,
+            n0 += 4 + wgrad(pfx + "self_attn.q_proj.weight", dqkv, xn1, (3 * H, H), span=3)
+            ops.rmsnorm_bwd(x, flat.pview(pfx + "input_layernorm.weight"), dxn1, rstd1, dx_mid, dx,
                             flat.gview(pfx + "input_layernorm.weight"), acc, ws_norm)
-            dx = dx_next
             n0 += 2
             if self.grad_ready_hook is not None and l in self._comm_slices(L):
                 # layers [l, hi) are final: their gradients form one contiguous slice of the bucket
@@ -587,13 +556,7 @@ class LlamaEngine:
                 hi_off = (flat.offsets[f"model.layers.{hi_l}.self_attn.q_proj.weight"][0] if hi_l < L
                           else flat.offsets["model.norm.weight"][0])
                 if lo_off < flat.n_train and hi_off <= flat.n_train and hi_off > lo_off:
-                    self.slice_ready_events = []
-                    if side is not None:  # the slice's weight gradients are final once the side stream reaches here
-                        ev = torch.cuda.Event()
-                        ev.record(side)
-                        self.slice_ready_events = [ev]
                     self.grad_ready_hook(lo_off, hi_off)
-                    self.slice_ready_events = []
 
         # splice + projector
         g_table = flat.gview("model.embed_tokens.weight", (V, H))
@@ -617,10 +580,6 @@ class LlamaEngine:
             if g_b is not None:
                 ops.colsum(daudio, g_b, accumulate=acc)
                 n0 += 1
-        if side is not None:  # join: the optimizer (main stream) reads the whole bucket
-            done = torch.cuda.Event()
-            done.record(side)
-            torch.cuda.current_stream().wait_event(done)
         flat.attach_grads()
         self.launches = n0
 

@@ -49,10 +49,8 @@ class LlarkAdamW(torch.optim.Optimizer):
         if not self.sync_gradients:
             return
         ev = torch.cuda.Event()
-        ev.record()  # on the compute stream: the slice is final once this point is reached ...
+        ev.record()  # on the compute stream: the slice is final once this point is reached
         self._comm_stream.wait_event(ev)
-        for side_ev in getattr(self.engine, "slice_ready_events", ()):  # ... and the wgrad side stream this one
-            self._comm_stream.wait_event(side_ev)
         self.comm.allreduce_(self.engine.flat.grads[start:end], stream=self._comm_stream)
         self._reduced.append((start, end))
 

@@ -369,36 +369,3 @@ def test_fp32_verification_mode_meets_the_1e3_logit_criterion(gold, gemm_mode, t
         print(f"\n[fp32 verify {gemm_mode}] logits rel-Frobenius {fro:.3e}, max-abs/max {mx:.3e}, loss rel {dl:.3e}")
     assert out.logits.dtype == torch.float32
     assert fro <= tol and mx <= tol and dl <= tol, (fro, mx, dl)
-
-
-def test_wgrad_side_stream_gives_bit_identical_gradients():
-    """The weight-gradient GEMMs run on a side stream (LlamaEngine.wgrad_stream_enabled): same kernels, same operands, so
-    every gradient -- first backward (overwrite), second backward (in-place accumulation), after an optimizer step -- is
-    bit-identical to the single-stream schedule, and no operand is recycled by the allocator while the side stream reads it
-    (a 6-layer model at widths where several GEMMs are in flight, repeated to give a race a chance to show)."""
-    from oracle import llama_oracle as lo
-    from llark_b200.optim import LlarkAdamW
-
-    cfg = lo.LlamaCfg(hidden_size=512, intermediate_size=1024, num_layers=6, num_heads=4, vocab_size=520,
-                      mm_hidden_size=96, audio_start_token=518, audio_end_token=519, audio_patch_token=517, pad_token=516)
-    params = lo.init_params(cfg, seed=4)
-    batch = _to_cuda(lo.make_batch(cfg, B=4, S=256, F_frames=7, seed=6))
-    results = []
-    for enabled in (False, True, True):
-        model = build_model(cfg, params)
-        model.engine.wgrad_stream_enabled = enabled
-        opt = LlarkAdamW(model, lr=1e-3)
-        snaps = []
-        for rounds in range(3):
-            model(**batch).loss.backward()
-            model(**batch).loss.backward()          # accumulates in place
-            torch.cuda.synchronize()
-            snaps.append({n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
-            opt.step()
-        snaps.append({n: p.detach().clone() for n, p in model.named_parameters()})
-        results.append(snaps)
-    for other in results[1:]:
-        for a, b in zip(results[0], other):
-            assert a.keys() == b.keys()
-            for n in a:
-                assert torch.equal(a[n], b[n]), n
