@@ -1,8 +1,9 @@
 """Model-level parity on the GPU: llark_b200.models.llamav2.WrappedLlamav2ForCausalLM (CUDA path through the
 C-ABI) against (a) the golden vectors produced by the REFERENCE's own class and (b) the oracle restatement run on
 CPU on the same seeded inputs. Tolerances (stated per assert): the reference trains in bf16, so two bf16 pipelines
-are compared by relative Frobenius norm (2e-2 on logits, 5e-2 on gradient norms, 2e-3 on the loss) and the CUDA
-path's error against the fp32 reference must not exceed the bf16 reference's own error by more than 50 %."""
+are compared by relative Frobenius norm and the CUDA path's error against the fp32 reference must not exceed the bf16
+reference's own error by more than 50 %. Bounds are ~2x the errors measured on a B200 in round 2
+(profiles/r2_parity_measured.txt: logits 4.5e-3 - 1.4e-2, gradients 8e-3 - 1.8e-2, in-place accumulation 2.5e-3)."""
 import os
 
 import pytest
@@ -44,7 +45,7 @@ def test_forward_backward_matches_reference_golden(gold, detach):
     assert abs(out.loss.item() - ref16["loss"].item()) < 2e-3 * ref16["loss"].item()
     valid = batch["attention_mask"]
     lg = out.logits.float().cpu()[valid]
-    check_close("test_forward_backward_matches_reference_golden:_rel_lg_ref16_logits_float_valid_", _rel(lg, ref16["logits"].float()[valid]), 2e-2)
+    check_close("test_forward_backward_matches_reference_golden:_rel_lg_ref16_logits_float_valid_", _rel(lg, ref16["logits"].float()[valid]), 1e-2)
     err_mine = _rel(lg, ref32["logits"][valid])
     err_ref = _rel(ref16["logits"].float()[valid], ref32["logits"][valid])
     assert err_mine < 1.5 * err_ref + 1e-3, (err_mine, err_ref)
@@ -57,7 +58,7 @@ def test_forward_backward_matches_reference_golden(gold, detach):
         assert g is not None, n
         assert abs(g.float().norm().item() - entry["norm"]) <= 5e-2 * max(entry["norm"], 1e-6), n
         if "full" in entry:
-            check_close(f"test_forward_backward_matches_reference_golden:_rel_g_float_entry_full_float_:{n}", _rel(g.float(), entry["full"].float()), 4e-2)
+            check_close(f"test_forward_backward_matches_reference_golden:_rel_g_float_entry_full_float_:{n}", _rel(g.float(), entry["full"].float()), 2e-2)
         if "nonzero_rows" in entry:
             rows = g.float().abs().sum(-1).nonzero().flatten().tolist()
             assert rows == entry["nonzero_rows"], n
@@ -94,25 +95,25 @@ def test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation():
     out.loss.backward()
     assert abs(out.loss.item() - loss_o.item()) < 3e-3 * loss_o.item()
     valid = batch["attention_mask"]
-    check_close("test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_out_logits_float_cpu_valid_logits_o", _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]), 2e-2)
+    check_close("test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_out_logits_float_cpu_valid_logits_o", _rel(out.logits.float().cpu()[valid], logits_o.float()[valid]), 1e-2)
     named = dict(model.named_parameters())
     for n, go in grads_o.items():
         if go is None:
             assert named[n].grad is None
             continue
-        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_go_float_:{n}", _rel(named[n].grad.float(), go.float()), 6e-2)
+        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_go_float_:{n}", _rel(named[n].grad.float(), go.float()), 2e-2)
     # second micro-batch accumulates in place (wgrad epilogue R = C): grads double
     g1 = {n: p.grad.float().clone() for n, p in named.items() if p.grad is not None}
     out2 = model(**cb)
     out2.loss.backward()
     for n, g in g1.items():
-        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_2_g_:{n}", _rel(named[n].grad.float(), 2 * g), 2e-2)
+        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_2_g_:{n}", _rel(named[n].grad.float(), 2 * g), 5e-3)
     # zero_grad(set_to_none) -> overwrite mode again
     model.zero_grad(set_to_none=True)
     out3 = model(**cb)
     out3.loss.backward()
     for n, g in g1.items():
-        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_g_:{n}", _rel(named[n].grad.float(), g), 1e-2)
+        check_close(f"test_matches_oracle_on_fresh_seed_with_list_encodings_and_accumulation:_rel_named_n_grad_float_g_:{n}", _rel(named[n].grad.float(), g), 1e-3)
 
 
 def test_value_errors_and_no_grad_forward(gold):
@@ -170,7 +171,7 @@ def test_llama7b_layer_shapes_run():
     named = dict(model.named_parameters())
     for n in ("model.mm_projector.weight", "model.layers.0.mlp.down_proj.weight", "model.layers.0.self_attn.q_proj.weight",
               "model.norm.weight"):
-        check_close(f"test_llama7b_layer_shapes_run:_rel_named_n_grad_float_grads_o_n_float_:{n}", _rel(named[n].grad.float(), grads_o[n].float()), 6e-2)
+        check_close(f"test_llama7b_layer_shapes_run:_rel_named_n_grad_float_grads_o_n_float_:{n}", _rel(named[n].grad.float(), grads_o[n].float()), 3.5e-2)
 
 
 def test_optimizer_step_then_backward_overwrites_stale_grads(gold):
@@ -201,7 +202,7 @@ def test_optimizer_step_then_backward_overwrites_stale_grads(gold):
     model(**batch).loss.backward()
     for n, p in model.named_parameters():
         if p.grad is not None:
-            check_close(f"test_optimizer_step_then_backward_overwrites_stale_grads:_rel_p_grad_float_2_g_a_n_:{n}", _rel(p.grad.float(), 2 * g_a[n]), 2e-2)
+            check_close(f"test_optimizer_step_then_backward_overwrites_stale_grads:_rel_p_grad_float_2_g_a_n_:{n}", _rel(p.grad.float(), 2 * g_a[n]), 5e-3)
 
 
 def test_generate_greedy_decoding_without_cache():
@@ -328,7 +329,7 @@ def test_frozen_backbone_projector_only_training_on_gpu(gold):
     _, _, grads_o = lo.forward_backward({k: v.to(torch.bfloat16) for k, v in params.items()}, cfg, batch)
     named = dict(model.named_parameters())
     for n in ("model.mm_projector.weight", "model.mm_projector.bias", "model.embed_tokens.weight"):
-        check_close(f"test_frozen_backbone_projector_only_training_on_gpu:_rel_named_n_grad_float_grads_o_n_float_:{n}", _rel(named[n].grad.float(), grads_o[n].float()), 6e-2)
+        check_close(f"test_frozen_backbone_projector_only_training_on_gpu:_rel_named_n_grad_float_grads_o_n_float_:{n}", _rel(named[n].grad.float(), grads_o[n].float()), 2e-2)
     assert all(p.grad is None for n, p in named.items() if "layers" in n or n in ("model.norm.weight", "lm_head.weight"))
     l0 = out.loss.item()
     for _ in range(3):

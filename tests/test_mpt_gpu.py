@@ -136,4 +136,4 @@ def test_mpt_engine_step_matches_oracle_on_gpu(F_frames, detach):
     named = dict(model.named_parameters())
     for name, g_ref in grads_o.items():
         assert named[name].grad is not None, name
-        check_close(f"test_mpt_engine_step_matches_oracle_on_gpu:_rel_named_name_grad_cpu_g_ref_:{name}", _rel(named[name].grad.cpu(), g_ref), 6e-2)
+        check_close(f"test_mpt_engine_step_matches_oracle_on_gpu:_rel_named_name_grad_cpu_g_ref_:{name}", _rel(named[name].grad.cpu(), g_ref), 4e-2)
