@@ -1282,6 +1282,19 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
             p.group_m = g < 2 ? 2 : (g > 32 ? 32 : g);
         }
     }
+    p.epi_a = ep ? ep->a : nullptr;
+    p.epi_b = ep ? ep->b : nullptr;
+    p.epi_ld = ep ? ep->ld : 0;
+    p.epi_i0 = ep ? ep->i0 : 0;
+    p.epi_i1 = ep ? ep->i1 : 0;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("LLARK_GEMM_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.debug = dbg;
+    }
 
     const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
     if (p.epi != LLARK_EPI_NONE) {
