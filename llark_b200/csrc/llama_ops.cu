@@ -227,30 +227,16 @@ __global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
 #pragma unroll
         for (int e = 0; e < 8; ++e) dwacc[i][e] = 0.f;
     }
-    // Two rows per iteration (rows blockIdx.x + 2k * gridDim.x and + gridDim.x beyond it): their loads are issued together
-    // and their two row sums share ONE block reduction, so twice the bytes are in flight per CTA. The per-row arithmetic
-    // and the order in which a CTA adds rows into its dw partial are unchanged (row a, then row b).
-    __shared__ float red2[32];
-    for (long long row = blockIdx.x; row < rows; row += 2LL * gridDim.x) {
-        const long long rowb = row + gridDim.x;
-        const bool hasb = rowb < rows;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const float rstd = rstd_in[row];
-        const float rstdb = hasb ? rstd_in[rowb] : 0.f;
-        float xh[VPT][8], g[VPT][8], xhb[VPT][8], gb[VPT][8];
-        float dot = 0.f, dotb = 0.f;
+        float xh[VPT][8], g[VPT][8];
+        float dot = 0.f;
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int c = (i * blockDim.x + threadIdx.x) * 8;
-            float xv[8], dyv[8], xvb[8], dyvb[8];
+            float xv[8], dyv[8];
             load8(x + row * H + c, xv);
             load8(dy + row * H + c, dyv);
-            if (hasb) {
-                load8(x + rowb * H + c, xvb);
-                load8(dy + rowb * H + c, dyvb);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) xvb[e] = dyvb[e] = 0.f;
-            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 xh[i][e] = xv[e] * rstd;
@@ -258,46 +244,20 @@ __global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
                 dot += g[i][e] * xh[i][e];
                 dwacc[i][e] += dyv[e] * bf16_round(xh[i][e]);
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                xhb[i][e] = xvb[e] * rstdb;
-                gb[i][e] = dyvb[e] * wv[i][e];
-                dotb += gb[i][e] * xhb[i][e];
-                dwacc[i][e] += dyvb[e] * bf16_round(xhb[i][e]);
-            }
         }
-        {   // one reduction round for both sums (same tree as block_sum for each of them)
-            dot = warp_sum(dot);
-            dotb = warp_sum(dotb);
-            const int wq = threadIdx.x >> 5, lq = threadIdx.x & 31, nw = blockDim.x >> 5;
-            __syncthreads();
-            if (lq == 0) {
-                red[wq] = dot;
-                red2[wq] = dotb;
-            }
-            __syncthreads();
-            dot = warp_sum(lq < nw ? red[lq] : 0.f) / (float)H;
-            dotb = warp_sum(lq < nw ? red2[lq] : 0.f) / (float)H;
-        }
+        dot = block_sum(dot, red) / (float)H;
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int c = (i * blockDim.x + threadIdx.x) * 8;
-            float o[8], ob[8];
-            if (dres) {
-                load8(dres + row * H + c, o);
-                if (hasb) load8(dres + rowb * H + c, ob);
-            } else {
+            float o[8];
+            if (dres) load8(dres + row * H + c, o);
+            else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = ob[e] = 0.f;
+                for (int e = 0; e < 8; ++e) o[e] = 0.f;
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += rstd * (g[i][e] - xh[i][e] * dot);
             store8(dx + row * H + c, o);
-            if (hasb) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ob[e] += rstdb * (gb[i][e] - xhb[i][e] * dotb);
-                store8(dx + rowb * H + c, ob);
-            }
         }
     }
 #pragma unroll
@@ -696,8 +656,9 @@ extern "C" int llark_rmsnorm_bwd(const void* x, const void* w, const void* dy, c
                                  void* dx, void* dw, int accumulate_dw, long long rows, int H, void* workspace,
                                  cudaStream_t st) {
     int t, v;
-    // small CTAs here too: 128 threads x 4 vectors x 2 rows keep 32 KB of loads in flight per CTA, two CTAs per SM
-    if (rows <= 0 || !norm_cfg(H, &t, &v, rows >= 1024) || !workspace) return LLARK_EINVAL;
+    // (measured, profiles/r2h_prof_opt_hbm.md: a two-rows-per-iteration variant on 128-thread CTAs ran at 2.5 TB/s against
+    // 3.7-4.5 TB/s for this one-row, 512-thread form -- 255 registers left 8 warps per SM -- so the backward keeps it)
+    if (rows <= 0 || !norm_cfg(H, &t, &v) || !workspace) return LLARK_EINVAL;
     const int nb = (int)(rows < 296 ? rows : 296);
     const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *wp = (const __nv_bfloat16*)w, *dyp = (const __nv_bfloat16*)dy,
                         *drp = (const __nv_bfloat16*)dres;
