@@ -239,7 +239,7 @@ def reference_step_fn(classes, model, B, device):
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
         opt.zero_grad(set_to_none=True)
-        loss = float(out.loss)
+        loss = float(out.loss.detach())
         sync()
         return t1 - t0, time.perf_counter() - t1, loss
 

@@ -719,7 +719,7 @@ extern "C" int llark_attn_bwd_rope(const void* qkv, const unsigned char* key_mas
 }
 
 // ---------------------------------------------------------------------------------------------- ALiBi (MPT variant)
-// STAGED (not yet run on a B200). Causal attention with key-padding mask and the ALiBi bias of MPT
+// Causal attention with key-padding mask and the ALiBi bias of MPT
 // (m2t/llava/model/mpt/attention.py:31-83, 458-484): scores = q.k / sqrt(128) + slopes[h] * (key - (S - 1)). Same layouts as
 // llark_attn_fwd / llark_attn_bwd (packed qkv without RoPE, LSE, Dsum workspace); tcgen05 kernels only (S <= 4096).
 extern "C" int llark_attn_alibi_fwd(const void* qkv, const unsigned char* key_mask, void* out, float* lse,

@@ -5,7 +5,7 @@
 // a 7B model), so it is written as an HBM-bound SIMT kernel instead: one warp per NCOL weight rows, every lane streams
 // 16-byte vectors of W (coalesced 512 B per warp and row), the M activation rows come from L1 / L2 (22 KB for K = 11008),
 // warp-shuffle reduction, deterministic. Algorithmic bytes per launch: 2 * N * K (+ 2 * M * (K + N)).
-// STAGED: compiled for sm_100a and used by LlamaEngine.decode_step (LLARK_KV_CACHE=1), not yet run on a B200.
+// Used by LlamaEngine.decode_step (the default path of generate()); first run on a B200 in round 2 (tests/test_kernels_gpu.py).
 #include "common.cuh"
 
 namespace llark {

@@ -4,8 +4,8 @@
 //   and the q_ln / k_ln LayerNorms of attention.py:248-251,289-292 -- both are "fp32 statistics, one rounding of the
 //   output to bf16", so one kernel serves both;
 //   exact GELU forward / backward (blocks.py:14, nn.GELU(approximate="none")).
-// STAGED: compiled for sm_100a and wired through llark_b200.ops / engine_mpt.py, whose schedule is verified on CPU against
-// the pinned oracle, but these kernels have not run on a B200 yet (tests gated by LLARK_STAGED=1).
+// Wired through llark_b200.ops / engine_mpt.py; per-op parity against fp32 references and the whole engine step against the
+// pinned oracle run on a B200 in tests/test_mpt_gpu.py (round 2).
 #include "common.cuh"
 #include <math.h>
 

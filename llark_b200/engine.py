@@ -385,8 +385,8 @@ class LlamaEngine:
         return loss, logits
 
     # ------------------------------------------------------------------------------------------ generation (KV cache)
-    # STAGED: compiled and unit-structured in round 1 but not yet run on a B200 (LLARK_KV_CACHE=1 enables it;
-    # tests/test_model_gpu.py::test_generate_with_kv_cache_matches_cacheless is gated on the same variable).
+    # Prefill + one-token decode steps against a KV cache: the default of generate() (LLARK_KV_CACHE=0 switches it off);
+    # verified on a B200 against the cache-less loop (tests/test_model_gpu.py::test_generate_with_kv_cache_matches_cacheless).
     def new_cache(self, B, s_max, device):
         cfg = self.cfg
         return KVCache(cfg.num_hidden_layers, B, s_max, cfg.hidden_size, device)

@@ -2,12 +2,13 @@
 buckets: what m2t/models/mpt.py WrappedMPTForCausalLM + m2t/llava/model/mpt/{modeling_mpt,blocks,attention,norm}.py
 compute, as a manual forward / backward over C-ABI ops.
 
-STATUS: STAGED. The schedule is verified on CPU against oracle/mpt_oracle.py (itself pinned to the reference's classes)
+STATUS: runs on the B200 since round 2 (tests/test_mpt_gpu.py in `pytest -m gpu`, tools/bench_mpt.py: 392 samples/s on one
+GPU, 757 on two). The schedule is verified on CPU against oracle/mpt_oracle.py (itself pinned to the reference's classes)
 with the test-only ops stand-in (tests/test_mpt_host_cpu.py). The ops only this variant calls -- `ln_fwd`, `ln_bwd`
 (bias-free LayerNorm, also over the q / k thirds of the packed qkv rows), `gelu_fwd`, `gelu_bwd` (csrc/mpt_ops.cu) and
 `attn_alibi_fwd/bwd` (csrc/attention_tc_alibi.cu: the tcgen05 attention with the per-head slope * (key - (S-1)) bias and
-no RoPE) -- compile for sm_100a but have not run on a B200 yet: tests/test_mpt_gpu.py (LLARK_STAGED=1) is their parity
-gate. There is no fallback: a failing kernel fails the step.
+no RoPE) -- have their per-op parity tests against fp32 references in tests/test_mpt_gpu.py. There is no fallback: a
+failing kernel fails the step.
 
 Per block (blocks.py:67-86), bf16 weights under bf16 autocast as m2t/train.py:101-103 sets up:
     a    = LN(x; norm_1)                         low-precision LayerNorm (norm.py:26-52), no bias (no_bias=True)

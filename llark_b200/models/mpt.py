@@ -3,9 +3,9 @@ and state-dict key names (`transformer.wte.weight`, `transformer.blocks.{i}.{nor
 attn.out_proj,norm_2,ffn.up_proj,ffn.down_proj}.weight`, `transformer.norm_f.weight`, `transformer.mm_projector.*`),
 so `m2t/train.py` takes its `"mpt" in model_name_or_path` branch over it unchanged.
 
-STATUS: STAGED. The modules hold parameters; `forward` runs llark_b200.engine_mpt.MPTEngine, whose schedule is verified
-on CPU against the pinned oracle; the kernels only this variant needs (mpt_ops.cu, attention_tc_alibi.cu) compile for
-sm_100a but have not run on a B200 yet (tests/test_mpt_gpu.py, LLARK_STAGED=1). Supported configuration = what MPT-1B uses: multi-head attention with
+STATUS: runs on the B200 since round 2. The modules hold parameters; `forward` runs llark_b200.engine_mpt.MPTEngine, whose
+schedule is verified against oracle/mpt_oracle.py on CPU (tests/test_mpt_host_cpu.py) and on the GPU kernels
+(tests/test_mpt_gpu.py, part of `pytest -m gpu`). Supported configuration = what MPT-1B uses: multi-head attention with
 ALiBi and q/k LayerNorm, low-precision LayerNorm, no biases, tied embeddings, no logit scale, attn_impl irrelevant."""
 from typing import List, Optional, Tuple
 

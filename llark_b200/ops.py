@@ -222,7 +222,7 @@ def attn_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, dqkv=None, 
 
 def gemv(x, w, bias=None, residual=None, out=None, N=None):
     """y[M, N] = x[M, K] @ w[N, K]^T (+ bias) (+ residual) for M <= 8 rows: the weight-streaming kernel of the decode step
-    (STAGED, see csrc/gemv.cu). `out` may be wider than N (padded logits buffer)."""
+    (csrc/gemv.cu). `out` may be wider than N (padded logits buffer)."""
     M, K = x.shape
     N = int(N) if N is not None else w.shape[0]
     out = out if out is not None else torch.empty((M, N), device=x.device, dtype=BF16)

@@ -395,7 +395,7 @@ def jb_pool_batched(acts, T_valid, frame):
     return acts[:, : n * frame].reshape(acts.shape[0], n, frame, -1).mean(2)
 
 
-# ------------------------------------------------------------------------------------------------ MPT variant (staged ops)
+# ------------------------------------------------------------------------------------------------ MPT variant
 def gemv(x, w, bias=None, residual=None, out=None, N=None):
     N = int(N) if N is not None else w.shape[0]
     y = x.float() @ w[:N].float().t()

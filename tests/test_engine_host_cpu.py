@@ -1,5 +1,5 @@
 """Host-logic tests of llark_b200.engine on CPU: the engine's forward schedule, the cache-less generate loop and the
-STAGED KV-cache path (prefill + decode steps, LLARK_KV_CACHE=1) are run with tests/cpu_ops.py standing in for the CUDA
+KV-cache path (prefill + decode steps) are run with tests/cpu_ops.py standing in for the CUDA
 ops (test infrastructure, see its header) and checked against the oracle. What this pins: flat-bucket views, splice
 bookkeeping, launch order, KV-cache indexing, the S=1 / offset-table RoPE of the decode step. What it cannot pin: the
 CUDA kernels (the `-m gpu` suite does)."""
@@ -70,7 +70,7 @@ def test_engine_forward_schedule_matches_oracle(cpu_engine):
         model(input_ids=bad, attention_mask=batch["attention_mask"], audio_encodings=batch["audio_encodings"])
 
 
-def test_generate_cacheless_and_staged_kv_cache_agree(cpu_engine, monkeypatch):
+def test_generate_cacheless_and_kv_cache_agree(cpu_engine, monkeypatch):
     from oracle import llama_oracle as lo
     from oracle.make_golden_generation import gen_inputs
 
