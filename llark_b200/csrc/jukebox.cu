@@ -8,6 +8,7 @@
 // (read x, write x'): the per-res-block fusion SURVEY §8(d) counts 1.42 GB/clip against.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace llark {
 
@@ -461,6 +462,186 @@ __device__ __forceinline__ void ja_load_rows(float* dst, const float* __restrict
         }
     }
 }
+// ---------------------------------------------------------------------------------------------- fused res block on tensor cores
+// The same ResConv1DBlock  y = x + W2 . relu(W1 (*dil d, k = 3) relu(x) + b1) + b2  (32 channels) as resblock_kernel, with
+// both convolutions as implicit GEMMs on mma.sync m16n8k8 TF32:  D[co, t] += A[co, k] . B[k, t],
+//   conv1: k = tap * 32 + ci (K = 96, 12 k-steps),  B[k, t] = relu(x)[ci, t + (tap - 1) d]   (shifted views of ONE smem tile)
+//   conv2: k = ci            (K = 32,  4 k-steps),  B[k, t] = relu(h)[ci, t]
+// and fp32 accuracy kept by the 3xTF32 split: every operand is hi + lo with hi = tf32(v), lo = tf32(v - hi), and
+// acc += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi (the dropped lo.lo term is ~2^-22 relative). The SIMT kernel runs at 20 TFLOP/s
+// (27 % of the FP32 pipe, FMA / LDS-issue bound, profiles/r2f_prof_jukebox_hbm.md); the tensor cores take the FMAs away.
+// CTA = 256 threads = 8 warps over a 256-step time tile; warp w owns time steps [32 w, 32 w + 32) (4 n-tiles of 8) and all
+// 32 output channels (2 m-tiles of 16). Shared memory:
+//   sx  relu(x) tile [32][LDX], LDX = in_w rounded up to 8 mod 32 so the B-fragment reads (4 rows x 8 columns per
+//       instruction) touch 32 different banks;
+//   sh  relu(h) / staging tile [32][LDH = 264], each warp touches only its own 32 columns (1x1 conv: no halo) -> __syncwarp;
+//   weights pre-split and stored FRAGMENT-MAJOR: [k-step][m-tile][lane][a0..a3 hi, a0..a3 lo], so a thread fetches the hi and
+//       lo A fragments of one (k-step, m-tile) with two conflict-free LDS.128.
+constexpr int RTC_TT = 256;
+constexpr int RTC_LDH = 264;
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(v);
+    lo = to_tf32(v - __uint_as_float(hi));
+}
+// w global [32 co][32 ci][KT]; frag [(ks * 2 + mt) * 32 + lane][8]; k = tap * 32 + ci
+template <int KT>
+__device__ __forceinline__ void load_weight_frags(float* frag, const float* __restrict__ w) {
+    constexpr int KS = KT * 4;  // k-steps of 8
+    for (int i = threadIdx.x; i < KS * 2 * 32 * 4; i += blockDim.x) {
+        const int r = i & 3, lane = (i >> 2) & 31, mt = (i >> 7) & 1, ks = i >> 8;
+        const int g = lane >> 2, t4 = lane & 3;
+        const int co = mt * 16 + g + (r & 1) * 8;
+        const int k = ks * 8 + t4 + (r >> 1) * 4;
+        const int tap = k >> 5, ci = k & 31;
+        const float v = w[(co * 32 + ci) * KT + tap];
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        float* dst = frag + (((ks * 2 + mt) * 32 + lane) << 3);
+        dst[r] = __uint_as_float(hi);
+        dst[4 + r] = __uint_as_float(lo);
+    }
+}
+__global__ void __launch_bounds__(256, 2)
+resblock_tc_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+                   const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int T, int d,
+                   int ldx) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int C = 32;
+    const int n = blockIdx.y;
+    const int t0 = blockIdx.x * RTC_TT;
+    const int in_w = RTC_TT + 2 * d;
+    float* f1 = sm;                       // conv1 weight fragments: 12 * 2 * 32 * 8
+    float* f2 = f1 + 12 * 2 * 32 * 8;     // conv2 weight fragments:  4 * 2 * 32 * 8
+    float* sh = f2 + 4 * 2 * 32 * 8;      // [C][RTC_LDH]
+    float* sx = sh + C * RTC_LDH;         // [C][ldx]
+    const float* xn = x + (long long)n * C * T;
+    // relu(x) tile, columns t0 - d .. t0 + 255 + d (zero outside [0, T)); eight independent loads per thread
+    for (int j = threadIdx.x; j < in_w; j += blockDim.x) {
+        const int ti = t0 - d + j;
+        const bool ok = ti >= 0 && ti < T;
+        const float* src = xn + (ok ? ti : 0);
+        for (int ci = 0; ci < C; ci += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ok ? src[(long long)(ci + u) * T] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sx[(ci + u) * ldx + j] = fmaxf(v[u], 0.f);
+        }
+    }
+    load_weight_frags<3>(f1, w1);
+    load_weight_frags<1>(f2, w2);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int tw = warp * 32;  // this warp's first time step inside the tile
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const float blo = b1[mt * 16 + g], bhi = b1[mt * 16 + g + 8];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            acc[mt][nt][0] = acc[mt][nt][1] = blo;
+            acc[mt][nt][2] = acc[mt][nt][3] = bhi;
+        }
+    }
+    // ---- conv1: 12 k-steps (tap-major), B from shifted columns of sx
+#pragma unroll 1
+    for (int ks = 0; ks < 12; ++ks) {
+        const int tap = ks >> 2, ci0 = (ks & 3) * 8;
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float4* fp = reinterpret_cast<const float4*>(f1 + (((ks * 2 + mt) * 32 + lane) << 3));
+            const float4 h = fp[0], l = fp[1];
+            ah[mt][0] = __float_as_uint(h.x); ah[mt][1] = __float_as_uint(h.y);
+            ah[mt][2] = __float_as_uint(h.z); ah[mt][3] = __float_as_uint(h.w);
+            al[mt][0] = __float_as_uint(l.x); al[mt][1] = __float_as_uint(l.y);
+            al[mt][2] = __float_as_uint(l.z); al[mt][3] = __float_as_uint(l.w);
+        }
+        const float* r0 = sx + (ci0 + t4) * ldx + tw + g + tap * d;
+        const float* r1 = r0 + 4 * ldx;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(r0[nt * 8], bh0, bl0);
+            split_tf32(r1[nt * 8], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_tf32(acc[mt][nt], al[mt], bh0, bh1);
+                mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
+                mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
+            }
+        }
+    }
+    // ---- relu(h) -> this warp's 32 columns of sh (accumulator layout: rows g / g + 8, columns 2 t4, 2 t4 + 1)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float* p0 = sh + (mt * 16 + g) * RTC_LDH + tw + nt * 8 + 2 * t4;
+            *reinterpret_cast<float2*>(p0) = make_float2(fmaxf(acc[mt][nt][0], 0.f), fmaxf(acc[mt][nt][1], 0.f));
+            *reinterpret_cast<float2*>(p0 + 8 * RTC_LDH) = make_float2(fmaxf(acc[mt][nt][2], 0.f), fmaxf(acc[mt][nt][3], 0.f));
+        }
+    __syncwarp();
+    // ---- conv2 (1x1): 4 k-steps, B from sh
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const float blo = b2[mt * 16 + g], bhi = b2[mt * 16 + g + 8];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            acc[mt][nt][0] = acc[mt][nt][1] = blo;
+            acc[mt][nt][2] = acc[mt][nt][3] = bhi;
+        }
+    }
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float4* fp = reinterpret_cast<const float4*>(f2 + (((ks * 2 + mt) * 32 + lane) << 3));
+            const float4 h = fp[0], l = fp[1];
+            ah[mt][0] = __float_as_uint(h.x); ah[mt][1] = __float_as_uint(h.y);
+            ah[mt][2] = __float_as_uint(h.z); ah[mt][3] = __float_as_uint(h.w);
+            al[mt][0] = __float_as_uint(l.x); al[mt][1] = __float_as_uint(l.y);
+            al[mt][2] = __float_as_uint(l.z); al[mt][3] = __float_as_uint(l.w);
+        }
+        const float* r0 = sh + (ks * 8 + t4) * RTC_LDH + tw + g;
+        const float* r1 = r0 + 4 * RTC_LDH;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(r0[nt * 8], bh0, bl0);
+            split_tf32(r1[nt * 8], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_tf32(acc[mt][nt], al[mt], bh0, bh1);
+                mma_tf32(acc[mt][nt], ah[mt], bl0, bl1);
+                mma_tf32(acc[mt][nt], ah[mt], bh0, bh1);
+            }
+        }
+    }
+    __syncwarp();  // every lane has finished reading relu(h) before the tile is reused as the output staging area
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float* p0 = sh + (mt * 16 + g) * RTC_LDH + tw + nt * 8 + 2 * t4;
+            *reinterpret_cast<float2*>(p0) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+            *reinterpret_cast<float2*>(p0 + 8 * RTC_LDH) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    __syncwarp();
+    // ---- y = x + (.): one channel row of this warp's 32 time steps per instruction (128 contiguous bytes)
+    const int t = t0 + tw + lane;
+    if (t < T) {
+#pragma unroll 8
+        for (int co = 0; co < C; ++co) {
+            const long long off = ((long long)n * C + co) * T + t;
+            y[off] = x[off] + sh[co * RTC_LDH + tw + lane];
+        }
+    }
+}
+
 template <int NKT>  // key tiles of 8 (8 -> 64 keys, 16 -> 128 keys)
 __global__ void __launch_bounds__(256)
 jb_sparse_attn_tc_kernel(const float* __restrict__ qkv, void* __restrict__ out, int out_bf16, int T, int heads, int dh,
@@ -699,6 +880,18 @@ extern "C" int llark_jb_conv_down(const float* x, const float* w, const float* b
 extern "C" int llark_jb_resblock(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                  float* y, int N, int T, int dilation, cudaStream_t st) {
     if (N <= 0 || T <= 0 || dilation < 1 || dilation > 243) return LLARK_EINVAL;
+    const char* tc_env = getenv("LLARK_JB_CONV_TC");  // "0" selects the fp32 SIMT kernel (read per call: tests toggle it)
+    const int use_tc = (tc_env && tc_env[0] == '0') ? 0 : 1;
+    if (use_tc && dilation <= 81) {
+        const int in_w = RTC_TT + 2 * dilation;
+        const int ldx = ((in_w + 23) / 32) * 32 + 8;  // >= in_w and == 8 (mod 32): conflict-free B-fragment reads
+        const int smem_tc = ((12 + 4) * 2 * 32 * 8 + 32 * RTC_LDH + 32 * ldx) * (int)sizeof(float);
+        int rc_tc = set_dyn_smem((const void*)resblock_tc_kernel, smem_tc);
+        if (rc_tc) return rc_tc;
+        dim3 grid_tc((T + RTC_TT - 1) / RTC_TT, N);
+        resblock_tc_kernel<<<grid_tc, 256, smem_tc, st>>>(x, w1, b1, w2, b2, y, T, dilation, ldx);
+        return jb_check();
+    }
     const int smem = (32 * (RES_TT + 2 * dilation) + 32 * RES_TT + 32 * 32 * 3 + 32 * 32) * (int)sizeof(float);
     int rc = set_dyn_smem((const void*)resblock_kernel, smem);
     if (rc) return rc;

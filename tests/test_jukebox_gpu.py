@@ -2,6 +2,7 @@
 restatement; network parity UNPINNED upstream, see its header) and against the reference's own windowed_average
 golden (tests/golden/pool_ref.pt). Tolerances: fp32 SIMT kernels 1e-4 rel; TF32 tensor-core GEMM path 5e-3 rel;
 bf16 mode 4e-2 rel; VQ codes equal except at near-ties (reported margin < 1e-4)."""
+import math
 import os
 
 import numpy as np
@@ -181,3 +182,33 @@ def test_label_conditioning_on_gpu_matches_oracle_and_feeds_the_prior():
         ref = jo.get_acts(wav[i], vq, opp, ocfg, meanpool=True, pool_frames_per_second=10)
         per_frame = (got[i] - ref).norm(dim=1) / ref.norm(dim=1)
         assert got[i].shape == ref.shape and (per_frame < 2e-2).float().mean().item() > 0.9
+
+
+@pytest.mark.parametrize("d", [1, 3, 9, 27])
+def test_resblock_tensor_core_kernel_matches_simt_and_fp64(d):
+    """The 3xTF32 mma.sync res-block (default) against the fp32 SIMT kernel (LLARK_JB_CONV_TC=0) and an fp64 conv1d
+    reference: both must sit at fp32 rounding level (the 3x split keeps ~22 mantissa bits), on a time length that is not a
+    multiple of the 256-step tile and with the dilation's halo crossing tile borders."""
+    import torch.nn.functional as F
+
+    from llark_b200 import ops
+
+    g = torch.Generator().manual_seed(d)
+    N, T = 2, 3000
+    x = torch.randn(N, 32, T, generator=g)
+    w1 = torch.randn(32, 32, 3, generator=g) / math.sqrt(96)
+    b1 = torch.randn(32, generator=g) * 0.1
+    w2 = torch.randn(32, 32, 1, generator=g) / math.sqrt(32)
+    b2 = torch.randn(32, generator=g) * 0.1
+    h = F.conv1d(F.relu(x.double()), w1.double(), b1.double(), padding=d, dilation=d)
+    ref = x.double() + F.conv1d(F.relu(h), w2.double(), b2.double())
+    args = [t.cuda().contiguous() for t in (x, w1, b1, w2, b2)]
+    os.environ["LLARK_JB_CONV_TC"] = "0"
+    try:
+        simt = ops.jb_resblock(*args, d).cpu()
+    finally:
+        os.environ.pop("LLARK_JB_CONV_TC", None)
+    tc = ops.jb_resblock(*args, d).cpu()
+    check_close(f"resblock_tc_vs_fp64:d{d}", _rel(tc, ref), 2e-6)
+    check_close(f"resblock_simt_vs_fp64:d{d}", _rel(simt, ref), 2e-6)
+    check_close(f"resblock_tc_vs_simt:d{d}", _rel(tc, simt), 2e-6)
