@@ -462,7 +462,8 @@ def jukebox_measure(precision="bf16", batch=8, steps=3, warmup=1, depth=36, objs
     conv_s = per_clip["conv_encoder"] / 1000.0
     return {"workload": "configs[1]: Jukebox front end only, 25 s @ 44.1 kHz synthetic clips -> [240,4800], batch %d, "
                         "1 GPU, levels 0/1 of the VQ-VAE skipped (dead work in the reference)" % batch,
-            "precision": {"conv_encoder": "fp32 SIMT" if not getattr(vqvae, "tensor_core", False) else "3xTF32 tcgen05",
+            "precision": {"conv_encoder": ("fp32 SIMT" if os.environ.get("LLARK_JB_CONV_TC") == "0" else
+                                           "res-blocks 3xTF32 mma.sync (fp32-equivalent), down / projection convs fp32 SIMT"),
                           "prior": precision}, "prior_depth": cfg.prior_depth,
             "clips_per_s": n / (total / 1000.0), "ms_per_clip": total / n, "ms_per_clip_by_stage": per_clip,
             "conv_encoder": {"fp32_tflops": 41.2e-3 / conv_s, "gbs_vs_1p42GB_per_clip": 1.42 / conv_s,
