@@ -470,10 +470,10 @@ __device__ __forceinline__ void epi_staged_bf16(const GemmParams& p, long long r
 
 // Epilogue of one 128 x 256 accumulator tile for the warp owning TMEM lanes [32 ew, 32 ew + 32): rows row0 .. row0 + 31.
 // The RoPE columns of a fused-QKV projection keep the row-per-thread path (rotation partners are 64 columns apart).
-// p.staged (chosen on the host, llark_gemm_ex) selects the staged path where the epilogue is the longer leg: fp32 output
-// and the SwiGLU backward. Plain bf16 output stays direct: its epilogue already hides behind the next tile's MMAs, and
-// the staging patch's extra 256 KB of shared-memory traffic per tile slows the operand pipeline by 3-4 % (same-box A/B,
-// profiles/r2c_epilogue_ab.md).
+// p.staged (chosen on the host, llark_gemm_ex) selects the staged path where the epilogue is the longer leg: a residual
+// with an fp32 tile or a short K, and the SwiGLU backward. Plain output at long K stays direct: its epilogue already hides
+// behind the next tile's MMAs, and the staging patch's extra 256 KB of shared-memory traffic per tile slows the operand
+// pipeline by 3-8 % (profiles/r2c_epilogue_ab.md, profiles/r2k_epilogue_probe.md).
 template <int EPI>
 __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, long long row0, int lane, int ncol0, uint32_t taddr,
                                                   float* stg) {
@@ -1261,7 +1261,14 @@ extern "C" int llark_gemm_ex(const void* A, int a_mn_major, long long lda, const
             const char* e = getenv("LLARK_GEMM_EPILOGUE");
             mode = (e && e[0] == 's') ? 1 : ((e && e[0] == 'd') ? 2 : 0);
         }
-        p.staged = mode == 1 ? 1 : (mode == 2 ? 0 : ((c_fp32 || p.epi == LLARK_EPI_SWIGLU_BWD) ? 1 : 0));
+        // auto: staged where the isolated-GEMM probe (tools/gemm_epilogue_probe.py, profiles/r2k_epilogue_probe.md) and
+        // the in-step A/B (profiles/r2c_epilogue_ab.md) measured it faster -- the SwiGLU backward; any residual with an fp32
+        // tile (K = 1200: 17.8 vs 21.6 us per tile, K = 4800: 35.8 vs 36.2) or with a short K (bf16, K = 1200: 12.8 vs 16.5);
+        // fp32 tiles without a residual only when K is short (K = 4800: direct 32.4 vs staged 35.1). Otherwise direct.
+        const bool short_k = (long long)K * eb < 2400LL * 2;  // fewer than ~2400 bf16-equivalent K elements
+        const bool want = p.epi == LLARK_EPI_SWIGLU_BWD || (R != nullptr && (c_fp32 || short_k)) ||
+                          (c_fp32 && R == nullptr && short_k);
+        p.staged = mode == 1 ? 1 : (mode == 2 ? 0 : (want ? 1 : 0));
     }
     {
         // Rasterisation group: tiles sweep n inside groups of `group_m` m-blocks, so a group's A panel
