@@ -23,6 +23,26 @@ BF16 = torch.bfloat16
 _ALIGN = 128  # elements (256 B): keeps every view 16-byte aligned for TMA and fused views gap-free
 
 
+class _Nvtx:
+    """NVTX ranges around the phases of a step (LLARK_NVTX=1; SURVEY section 5 tracing): `llark.forward`, `llark.backward`,
+    `llark.layer_fwd[l]` / `llark.layer_bwd[l]`, and `llark.optimizer` (optim.py), so `ncu --nvtx --nvtx-include` and any
+    timeline tool can cut a capture down to one phase or one layer. Off by default: two calls per range otherwise."""
+    on = os.environ.get("LLARK_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.on and torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _Nvtx.on and torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class FlatBuckets:
     """Packs a list of (name, nn.Parameter) into one flat bf16 buffer, trainable parameters first."""
 
@@ -140,14 +160,16 @@ class _StepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, engine, batch):
-        loss, logits = engine._forward(batch, need_grad=True)
+        with _Nvtx("llark.forward"):
+            loss, logits = engine._forward(batch, need_grad=True)
         ctx.engine = engine
         ctx.mark_non_differentiable(logits)
         return loss, logits
 
     @staticmethod
     def backward(ctx, dloss, _dlogits):
-        ctx.engine._backward(dloss)
+        with _Nvtx("llark.backward"):
+            ctx.engine._backward(dloss)
         return None, None, None
 
 
@@ -350,7 +372,8 @@ class LlamaEngine:
         recompute = need_grad and self._want_recompute(M, dev)
         self.recomputed_last_step = recompute
         for l in range(L):
-            x_out, keep, n = self._layer_forward(l, x, mask_u8, B, S, cos, sin, kv_sink)
+            with _Nvtx(f"llark.layer_fwd[{l}]"):
+                x_out, keep, n = self._layer_forward(l, x, mask_u8, B, S, cos, sin, kv_sink)
             n0 += n
             if need_grad:
                 # with recompute only the layer's input survives the forward; _backward regenerates the rest
@@ -504,6 +527,7 @@ class LlamaEngine:
         cos, sin = self._tables(S, dev)
 
         for l in reversed(range(L)):
+            nv = _Nvtx(f"llark.layer_bwd[{l}]").__enter__()
             pfx = f"model.layers.{l}."
             kept = sv["layers"][l]
             sv["layers"][l] = None
@@ -557,6 +581,7 @@ class LlamaEngine:
                           else flat.offsets["model.norm.weight"][0])
                 if lo_off < flat.n_train and hi_off <= flat.n_train and hi_off > lo_off:
                     self.grad_ready_hook(lo_off, hi_off)
+            nv.__exit__()
 
         # splice + projector
         g_table = flat.gview("model.embed_tokens.weight", (V, H))

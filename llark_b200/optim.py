@@ -56,6 +56,12 @@ class LlarkAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        from .engine import _Nvtx
+
+        with _Nvtx("llark.optimizer"):
+            return self._step()
+
+    def _step(self):
         flat = self.engine.flat
         if id(flat) != self._flat_id:
             raise RuntimeError("the model was re-packed after the optimizer was created; build the optimizer last")
