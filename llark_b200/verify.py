@@ -29,6 +29,11 @@ def _linear(x, w, bias=None, residual=None, mode="3xtf32"):
     return ops.gemm(x_hi, w_hi, residual=y, bias=bias, out=y)
 
 
+def _require_cuda(dev):
+    if dev.type != "cuda":
+        raise RuntimeError("llark_b200 has no CPU path: move the model to a CUDA device (B200) first")
+
+
 @torch.no_grad()
 def forward_fp32(lm, input_ids, attention_mask=None, labels=None, audio_encodings=None):
     """(loss or None, logits fp32 [B, S, V]) of WrappedLlamav2ForCausalLM `lm` computed in fp32 on the GPU."""
@@ -38,8 +43,7 @@ def forward_fp32(lm, input_ids, attention_mask=None, labels=None, audio_encoding
     cfg = lm.config
     P = {n: p.detach().to(F32).contiguous() for n, p in lm.named_parameters()}
     dev = P["model.embed_tokens.weight"].device
-    if dev.type != "cuda":
-        raise RuntimeError("llark_b200 has no CPU path: move the model to a CUDA device (B200) first")
+    _require_cuda(dev)
     ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
     B, S = ids.shape
     H, L, NH = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads

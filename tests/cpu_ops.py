@@ -474,3 +474,55 @@ def attn_alibi_bwd(qkv, key_mask, out, dout, lse, B, S, n_heads, head_dim, slope
         o, _ = _alibi_attention(x, key_mask, B, S, n_heads, head_dim, slopes)
         o.backward(dout.float())
     return x.grad.to(BF16)
+
+
+# ------------------------------------------------------------------------------------------------ fp32 verification path
+# stand-ins for llark_b200.ops.v32_* (csrc/verify_fp32.cu): plain fp32 PyTorch, so tests/test_verify_host_cpu.py can check
+# the SCHEDULE of llark_b200/verify.py (what is composed from what, in which order) against the reference's fp32 golden
+def v32_split_tf32(x):
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)   # 13 low mantissa bits cleared (0xffffe000)
+    return hi, x - hi
+
+
+def v32_embed_splice_fwd(ids, table, audio, audio_off, frames, start_pos, out):
+    B, S = ids.shape
+    for b in range(B):
+        out[b] = table[ids[b].clamp(0, table.shape[0] - 1)]
+        p = int(start_pos[b]) if start_pos is not None else -1
+        if p >= 0:
+            F_ = int(frames[b])
+            out[b, p + 1: p + 1 + F_] = audio[int(audio_off[b]): int(audio_off[b]) + F_]
+    return out
+
+
+def v32_rmsnorm_fwd(x, w, eps):
+    return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+
+
+def v32_rope_(qkv, cos_t, sin_t, S, n_rot_heads, D):
+    rows = torch.arange(qkv.shape[0]) % S
+    v = qkv[:, : n_rot_heads * D].view(qkv.shape[0], n_rot_heads, D)
+    c, s = cos_t[rows][:, None, :], sin_t[rows][:, None, :]
+    rot = torch.cat((-v[..., D // 2:], v[..., : D // 2]), dim=-1)
+    v.copy_(v * c + rot * s)
+    return qkv
+
+
+def v32_swiglu_fwd(gu):
+    I = gu.shape[1] // 2
+    return torch.nn.functional.silu(gu[:, :I]) * gu[:, I:]
+
+
+def v32_attn_fwd(qkv, key_mask, B, S, n_heads, head_dim):
+    q, k, v = qkv.view(B, S, 3, n_heads, head_dim).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(head_dim)
+    allow = torch.ones(S, S, dtype=torch.bool).tril()[None, None]
+    if key_mask is not None:
+        allow = allow & key_mask.view(B, 1, 1, S).bool()
+    p = torch.softmax(sc.masked_fill(~allow, float("-inf")), dim=-1).nan_to_num(0.0)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * S, n_heads * head_dim)
+
+
+def v32_ce_fwd(logits, V, labels, B, S):
+    lg = logits.view(B, S, -1)[:, :, :V]
+    return torch.nn.functional.cross_entropy(lg[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1), ignore_index=-100)
