@@ -150,19 +150,32 @@ class PriorTransformer:
     """`top_prior.prior`: ConditionalAutoregressive2D restricted to what LLark calls (only_encode forward)."""
 
     def __init__(self, cfg, state, device="cuda", precision="tf32"):
-        if precision not in ("tf32", "bf16"):
-            raise ValueError("precision must be 'tf32' (parity mode: fp32 storage, TF32 tensor cores) or 'bf16'")
+        if precision not in ("tf32", "bf16", "3xtf32"):
+            raise ValueError("precision must be 'tf32' (fp32 storage, single-pass TF32 tensor cores), '3xtf32' (fp32 storage, "
+                             "every product composed from TF32 halves: fp32-equivalent, what the reference's fp16=False "
+                             "forward computes, at three GEMM passes per linear) or 'bf16'")
         self.cfg, self.device, self.precision = cfg, torch.device(device), precision
         self.only_encode = False
-        wdt = torch.float32 if precision == "tf32" else BF16
+        wdt = BF16 if precision == "bf16" else torch.float32
         self.w = {}
         for k, v in state.items():
             v = v.to(self.device, torch.float32)
             if k.endswith((".c_attn.w", ".c_proj.w", ".fc.w", ".fc_proj.w")):
                 v = v.t().contiguous().to(wdt)  # Conv1D [n_in, n_out] -> K-major [n_out, n_in]
             self.w[k] = v.contiguous()
+        if precision == "3xtf32":  # frozen weights: split once into hi (exactly TF32-representable) + lo
+            for k in [k for k in self.w if k.endswith((".c_attn.w", ".c_proj.w", ".fc.w", ".fc_proj.w"))]:
+                self.w[k + "_hi"], self.w[k + "_lo"] = ops.v32_split_tf32(self.w[k])
 
     def _lin(self, x, name, residual=None):
+        if self.precision == "3xtf32":
+            # x.W = x_lo.W_hi + x_hi.W_lo + x_hi.W_hi accumulated in fp32 through the GEMM's residual input (small terms
+            # first); the dropped lo.lo term is ~2^-22 relative
+            w_hi, w_lo = self.w[name + ".w_hi"], self.w[name + ".w_lo"]
+            x_hi, x_lo = ops.v32_split_tf32(x)
+            y = ops.gemm(x_lo, w_hi, residual=residual, out_dtype=torch.float32)
+            y = ops.gemm(x_hi, w_lo, residual=y, out=y)
+            return ops.gemm(x_hi, w_hi, residual=y, bias=self.w[name + ".b"], out=y)
         return ops.gemm(x, self.w[name + ".w"], bias=self.w[name + ".b"], residual=residual,
                         out_dtype=torch.float32)
 
@@ -179,20 +192,24 @@ class PriorTransformer:
         xc = (x_cond if x_cond is not None else w["x_cond"]).reshape(-1, cfg.prior_width)[:T].contiguous().float()
         yc = (y_cond if y_cond is not None else w["y_cond"]).reshape(-1)[: cfg.prior_width].contiguous().float()
         h = ops.jb_embed_tokens(x.to(self.device).contiguous(), w["x_emb"], yc, w["pos_emb"], xc)  # [N*T, W]
-        act_dt = torch.float32 if self.precision == "tf32" else BF16
+        act_dt = BF16 if self.precision == "bf16" else torch.float32
+        exact = self.precision == "3xtf32"  # fp32 SIMT factored attention instead of the TF32 tensor-core kernel
         dh = cfg.attn_width // cfg.heads
         bc = T // cfg.blocks if cfg.blocks <= T else T
         for d in range(cfg.prior_depth):
             q = f"blk.{d}"
             n0 = ops.layernorm_fwd(h, w[q + ".ln0.g"], w[q + ".ln0.b"], cfg.ln_eps, out_dtype=act_dt)
             qkv = self._lin(n0, q + ".c_attn")
-            a = ops.jb_sparse_attn(qkv, N, T, cfg.heads, dh, bc, d % 3, out_dtype=act_dt)  # cast fused (bf16 prior)
+            a = ops.jb_sparse_attn(qkv, N, T, cfg.heads, dh, bc, d % 3, out_dtype=act_dt, exact=exact)  # cast fused (bf16)
             if a.dtype != act_dt:
                 a = ops.cast_f32_to_bf16(a)
             xa = self._lin(a, q + ".c_proj", residual=h)  # x + a
             n1 = ops.layernorm_fwd(xa, w[q + ".ln1.g"], w[q + ".ln1.b"], cfg.ln_eps, out_dtype=act_dt)
             # quick-GELU (and the bf16 cast of the bf16 prior) fused into the fc GEMM's epilogue
-            m = ops.gemm(n1, w[q + ".fc.w"], bias=w[q + ".fc.b"], out_dtype=act_dt, quick_gelu=True)
+            if exact:
+                m = ops.quick_gelu(self._lin(n1, q + ".fc"))
+            else:
+                m = ops.gemm(n1, w[q + ".fc.w"], bias=w[q + ".fc.b"], out_dtype=act_dt, quick_gelu=True)
             h = self._lin(m, q + ".fc_proj", residual=xa)  # (x + a) + m
         return h.view(N, T, cfg.prior_width)
 

@@ -102,3 +102,24 @@ def test_load_model_from_upstream_format_checkpoints(cpu_jukebox, tmp_path):
     # the name maps of the product and of the oracle are the same table
     assert jmodel.vqvae_key_map(cfg) == jo.upstream_vqvae_keys(ocfg)
     assert jmodel.prior_key_map(cfg) == jo.upstream_prior_keys(ocfg)
+
+
+def test_prior_3xtf32_schedule_matches_the_oracle(cpu_jukebox):
+    """precision="3xtf32" (fp32-equivalent prior: every linear composed from TF32 halves, fp32 SIMT attention, separate
+    quick-GELU): the host schedule over the CPU stand-ins reproduces the oracle's fp32 prior to rounding level."""
+    from oracle import jukebox_oracle as jo
+
+    jm, jmodel = cpu_jukebox
+    ocfg = jo.tiny_cfg()
+    cfg = jmodel.JukeboxConfig(sample_length=ocfg.sample_length, l_bins=ocfg.l_bins, n_ctx=ocfg.n_ctx,
+                               prior_width=ocfg.prior_width, prior_depth=ocfg.prior_depth, heads=ocfg.heads,
+                               m_attn=ocfg.m_attn, blocks=ocfg.blocks)
+    pp = jo.init_prior_params(ocfg, seed=1)
+    codes = torch.randint(0, ocfg.l_bins, (2, ocfg.n_ctx), generator=torch.Generator().manual_seed(9))
+    ref = jo.prior_forward(codes, pp, ocfg)
+    tp = jmodel.JukeboxTopPrior(cfg, pp, device="cpu", precision="3xtf32")
+    tp.prior.only_encode = True
+    out = tp.prior.forward(codes, x_cond=None, y_cond=None, encoder_kv=None, fp16=False)
+    assert out.dtype == torch.float32 and ((out - ref).norm() / ref.norm()).item() < 1e-5
+    with pytest.raises(ValueError):
+        jmodel.PriorTransformer(cfg, pp, device="cpu", precision="fp64")
