@@ -59,7 +59,7 @@ def test_conv_encoder_and_vq_match_oracle():
     assert (codes2 != codes_o).float().mean().item() < 1e-3
 
 
-@pytest.mark.parametrize("precision,tol", [("3xtf32", 2e-5), ("tf32", 5e-3), ("bf16", 4e-2)])
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 2e-5), ("tf32", 5e-3), ("bf16", 1.5e-2)])
 def test_prior_forward_matches_oracle(precision, tol):
     jo, ocfg, cfg = _cfgs()
     from llark_b200.jukebox.model import JukeboxTopPrior
