@@ -348,7 +348,7 @@ def run_reference(args):
                              "sample": m["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def gpu_torch_baseline(B, steps, warmup):
@@ -576,8 +576,19 @@ def measure_extras(args, model, opt, B, world, rank, timed):
     return out
 
 
+_REAL_STDOUT = sys.stdout
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else the run prints (the reference's own
+    `[INFO] ...` prints during model construction, warnings) is routed to stderr by main()."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse()
+    sys.stdout = sys.stderr  # keep stdout clean for the JSON line (see emit)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -778,7 +789,7 @@ def main():
         except Exception as e:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port",
                                     "sample": f"failed: {e!r}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         import torch.distributed as dist
 
